@@ -52,6 +52,70 @@ int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_t nq, int64
                       float* scores, int64_t ld_scores, void* workspace, size_t workspace_bytes,
                       cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Ranking passes shared by K1 and KR. Recall@K in the reference is `gt in torch.topk(row, k)` per row
+ * (main.py:331-378, v28 :203-229); outside exact fp32 ties that is  #{j : S[q,j] > thr_q} < k  with
+ * thr_q = max_{c in GT(q)} S[q,c]  (SURVEY 5.3). Ground truth is CSR: gt_idx[gt_off[q] .. gt_off[q+1]) are GLOBAL
+ * gallery column indices; g_base is the global index of this call's column 0 (gallery shard offset).
+ *   MMX_MODE_THRESHOLD  thr[q] = max(thr[q], S[q, c - g_base]) over the GT columns inside this shard.
+ *                       The caller fills thr with -inf first; shards are combined with a max.
+ *   MMX_MODE_COUNT      cnt_above[q] += #{j < ng : S[q,j] > thr[q]}  (caller zeroes cnt_above first);
+ *                       above_bits (nullable, [nq, words_per_row] uint32): bit j of word w = S[q, 32w+j] > thr[q].
+ */
+#define MMX_MODE_THRESHOLD 0
+#define MMX_MODE_COUNT 1
+
+/* K1  dense similarity + rank — replaces torch.matmul(txt.float(), img.float().t()) at main.py:473 (v28 :390-391)
+ * fused with the metric loops above. Q [nq, d] and G [ng, d] are bf16 row-major (ld = d, d % 8 == 0); products are
+ * exact in fp32 and accumulated in fp32 on tcgen05. `scores` (nullable, fp32 [nq, ld_scores]) is only written in
+ * MMX_MODE_COUNT and only when the caller needs the matrix itself (compute_similarity_scores drop-in).
+ * workspace (MMX_MODE_THRESHOLD only): mmx_dense_workspace_bytes(nq, ng). */
+int mmx_dense_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes);
+int mmx_dense_rank(const void* Q, int64_t nq, const void* G, int64_t ng, int d, const int32_t* gt_off,
+                   const int32_t* gt_idx, int64_t g_base, int mode, float* thr, int32_t* cnt_above,
+                   uint32_t* above_bits, int64_t words_per_row, float* scores, int64_t ld_scores, void* workspace,
+                   size_t workspace_bytes, cudaStream_t stream);
+
+/* KR  the same two passes over a materialised fp32 score matrix [nq, ng] (row pitch ld) — what
+ * compute_metrics_detailed (main.py:305-383) / compute_metrics (v28 :203-229) receive, and what K2 produces. */
+int mmx_rank_from_scores(const float* scores, int64_t nq, int64_t ng, int64_t ld, const int32_t* gt_off,
+                         const int32_t* gt_idx, int64_t g_base, int mode, float* thr, int32_t* cnt_above,
+                         uint32_t* above_bits, int64_t words_per_row, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K3  bootstrap — replaces the resample/gather/rescore/metrics loop of main.py:586-634 by the multiplicity
+ * identity of SURVEY 5.4 on the BASE score pass:
+ *     m = bincount(sample_indices[b]);  c_q = sum_col m[col2unit[col]] * above[q, col];
+ *     correct[b, k] = sum_q min(m[q_unit[q]], max(0, k - c_q)),  k in {1, 5, 10}.
+ * mmx_bincount:     sample_idx int32 [B, n_draws] (the reference's np.random.choice(N, N) draws, main.py:588)
+ *                   -> mult uint8 [B, n_units], saturated at 255 (exact: only min(., 10) is ever used);
+ *                   scratch int32 [B, n_units].
+ * mmx_above_lists:  first L set columns of every bitmask row, mapped through col2unit (nullable = identity),
+ *                   stored transposed: list_t[i * nq + q].
+ * mmx_boot_counts:  correct int32 [B, 3]. A row whose list was truncated (cnt_above > L) and ran out before the
+ *                   running multiplicity reached 10 is recounted exactly from its bitmask row.
+ *                   q_hits1 (nullable int32 [nq], caller-zeroed) += the query's R@1 hits over all iterations: the
+ *                   `correct_r1` bits that aggregate_failure_analysis (main.py:669-722) sums per caption feature.
+ */
+int mmx_bincount(const int32_t* sample_idx, int B, int64_t n_draws, int64_t n_units, int32_t* scratch, uint8_t* mult,
+                 cudaStream_t stream);
+int mmx_above_lists(const uint32_t* above_bits, int64_t nq, int64_t words_per_row, const int32_t* col2unit, int L,
+                    int32_t* list_t, cudaStream_t stream);
+int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_above, const uint32_t* above_bits,
+                    int64_t words_per_row, const int32_t* col2unit, const int32_t* q_unit, const uint8_t* mult, int B,
+                    int64_t n_units, int64_t nq, int32_t* correct, int32_t* q_hits1, cudaStream_t stream);
+
+/* K4  CI resample means — replaces the 10 000 x (np.random.choice(data, n) ; np.mean) loop of main.py:268-270.
+ * idx int32 [R, n] is the reference's index stream (RandomState.randint(0, n, (R, n)) == R x choice);
+ * means[r] = np.mean(data[idx[r]]) bit for bit (fp64, numpy's pairwise summation order). */
+int mmx_ci_means(const double* data, int n, const int32_t* idx, int R, double* means, cudaStream_t stream);
+
+/* K5  permutation statistics — replaces the shuffle + two means loop of main.py:295-299.
+ * perm int32 [P, n1+n2] are the cumulative np.random.shuffle states of an index array;
+ * diffs[p] = |np.mean(combined[perm[p, :n1]]) - np.mean(combined[perm[p, n1:]])| bit for bit. */
+int mmx_perm_stats(const double* combined, int n1, int n2, const int32_t* perm, int P, double* diffs,
+                   cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,12 +68,14 @@ _SIGNATURES = {
         _c.c_void_p, _c.c_int64,                               # scores, ld_scores
         _c.c_void_p, _c.c_size_t, _c.c_void_p,                 # workspace, bytes, stream
     ]),
+    "mmx_dense_workspace_bytes": (_c.c_int, [_c.c_int64, _c.c_int64, _c.POINTER(_c.c_size_t)]),
     "mmx_dense_rank": (_c.c_int, [
         _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int,   # Q, nq, G, ng, d
         _c.c_void_p, _c.c_void_p, _c.c_int64,                         # gt_off, gt_idx, g_base
         _c.c_int, _c.c_void_p,                                        # mode, thr
         _c.c_void_p, _c.c_void_p, _c.c_int64,                         # cnt_above, above_bits, words_per_row
-        _c.c_void_p, _c.c_int64, _c.c_void_p,                         # scores, ld_scores, stream
+        _c.c_void_p, _c.c_int64,                                      # scores, ld_scores
+        _c.c_void_p, _c.c_size_t, _c.c_void_p,                        # workspace, bytes, stream
     ]),
     "mmx_rank_from_scores": (_c.c_int, [
         _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int64,              # scores, nq, ng, ld
@@ -81,15 +83,16 @@ _SIGNATURES = {
         _c.c_int, _c.c_void_p,                                        # mode, thr
         _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p,            # cnt_above, above_bits, words_per_row, stream
     ]),
-    "mmx_mult_planes": (_c.c_int, [
-        _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int64,   # mult[B,n_units], B, n_units, col2unit, n_cols
-        _c.c_int, _c.c_void_p, _c.c_int64, _c.c_void_p,               # planes, out, words_per_row, stream
+    "mmx_bincount": (_c.c_int, [
+        _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,  # idx,B,n_draws,n_units,scratch,mult,stream
+    ]),
+    "mmx_above_lists": (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,  # bits,nq,wpr,col2unit,L,list_t,stream
     ]),
     "mmx_boot_counts": (_c.c_int, [
-        _c.c_void_p, _c.c_int64, _c.c_int64,                          # above_bits, nq, words_per_row
-        _c.c_void_p, _c.c_int, _c.c_int,                              # mult_planes, planes, B
-        _c.c_void_p, _c.c_void_p, _c.c_int64,                         # q_unit, mult, n_units
-        _c.c_void_p, _c.c_void_p,                                     # correct[B,3] (int64), stream
+        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_int64,  # list_t, L, cnt_above, bits, wpr
+        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64,  # col2unit, q_unit, mult, B, n_units
+        _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,            # nq, correct, q_hits1, stream
     ]),
     "mmx_ci_means": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,   # data, n, idx, R, means, stream

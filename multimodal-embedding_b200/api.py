@@ -1,0 +1,369 @@
+"""Host side of the drop-in boundary: the reference's own Python signatures, backed by libmmx.so.
+
+Same names, argument meaning, return types and error behaviour (ordinary Python exceptions, never sys.exit) as
+/root/reference/main.py: ``compute_similarity_scores`` (:440), ``compute_metrics_detailed`` (:305),
+``bootstrap_confidence_interval`` (:259), ``permutation_test`` (:281), ``run_bootstrap_benchmark`` (:478) and v28's
+``compute_metrics`` (run_benchmark_grand_slam_v28_publication_ready.py:203). Inputs are the caller's CPU tensors,
+outputs are CPU tensors / Python floats; the work happens on the current CUDA device through libmmx.
+
+Plus the fused fast path the harness times: ``score_and_rank`` -> device-resident rank structures without
+a score matrix, ``bootstrap_from_ranks`` -> per-iteration integer counts, ``run_bootstrap_from_embeddings`` -> CSV row.
+
+Random numbers: exactly like the reference these functions consume numpy's legacy MT19937 stream — the GLOBAL
+``np.random`` state unless an explicit ``RandomState`` is passed — in the reference's order, in bulk
+(``randint(0, n, (R, n))`` is the same stream as R calls of ``choice``).
+"""
+from __future__ import annotations
+
+import time
+from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .failure import (aggregate_failure_analysis, aggregate_failure_from_hits, analyze_query_complexity,
+                      get_category_from_caption)
+
+KS = (1, 5, 10)
+METRIC_KEYS = [f"{p}_R@{k}" for p in ("T2I", "I2T", "I2T_Sym") for k in KS]     # main.py:358,368,378
+CSV_COLUMNS = (["Model"] + [f"{k}_{s}" for k in METRIC_KEYS for s in ("mean", "lower", "upper", "std")]
+               + ["Time", "QPS", "Encoding_Time", "Img_per_sec", "_failure_analysis"])  # main.py:643-665
+N_BOOTSTRAP = 10000       # main.py:265
+CHUNK = 10                # main.py:453
+
+
+# ------------------------------------------------------------------------------------------------ plumbing
+def _device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.MmxError("no CUDA device: the scoring path has no CPU fallback")
+    _lib.lib()  # fail loudly if libmmx.so was not built
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _h2d(t: torch.Tensor, dev: torch.device, dtype=None) -> torch.Tensor:
+    """Host tensor -> device through pinned memory (async on the current stream)."""
+    if t.is_cuda:
+        return t if dtype is None or t.dtype == dtype else t.to(dtype)
+    t = t.contiguous()
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not t.is_pinned():
+        p = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        p.copy_(t)
+        t = p
+    return t.to(dev, non_blocking=True)
+
+
+def _np_h2d(a: np.ndarray, dev: torch.device, dtype: torch.dtype) -> torch.Tensor:
+    return _h2d(torch.from_numpy(np.ascontiguousarray(a)), dev, dtype)
+
+
+def _as_bf16(t: torch.Tensor, what: str) -> torch.Tensor:
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"{what}: expected torch.bfloat16 embeddings (the reference's DTYPE on a bf16 GPU, "
+                        f"main.py:93), got {t.dtype}")
+    return t
+
+
+def _as_list(x: Union[torch.Tensor, Sequence[torch.Tensor]]) -> List[torch.Tensor]:
+    """ColPali side as a list of [L_i, 128] tensors (v28 semantics; a padded [n, L, 128] tensor is split per item)."""
+    if isinstance(x, torch.Tensor):
+        if x.dim() != 3:
+            raise ValueError("ColPali embeddings must be a list of [L_i, 128] tensors or one padded [n, L, 128] tensor")
+        return [x[i] for i in range(x.size(0))]
+    out = []
+    for t in x:
+        out.append(t[0] if t.dim() == 3 and t.size(0) == 1 else t)
+    return out
+
+
+def _flatten(items: List[torch.Tensor], dev: torch.device) -> Tuple[torch.Tensor, torch.Tensor, np.ndarray]:
+    lens = np.array([int(t.shape[0]) for t in items], dtype=np.int64)
+    off = np.zeros(len(items) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(lens)
+    flat = torch.cat([_as_bf16(t, "ColPali embeddings") for t in items], dim=0) if items else torch.empty(0, 128, dtype=torch.bfloat16)
+    return _h2d(flat, dev), _np_h2d(off, dev, torch.int32), lens
+
+
+def _pad_flags(lens: np.ndarray, chunk: int = CHUNK) -> np.ndarray:
+    """1 where pad_sequence adds a zero row to the document inside its chunk of 10 (main.py:465-467)."""
+    flags = np.zeros(len(lens), dtype=np.uint8)
+    for j in range(0, len(lens), chunk):
+        c = lens[j:j + chunk]
+        flags[j:j + chunk] = (c < c.max()).astype(np.uint8)
+    return flags
+
+
+def _gt_dev(gt_sets: Sequence[Sequence[int]], dev: torch.device):
+    off, idx = ops.csr_from_sets(gt_sets)
+    return _np_h2d(off, dev, torch.int32), _np_h2d(idx, dev, torch.int32)
+
+
+def _identity_gt(n: int, dev: torch.device):
+    return (torch.arange(n + 1, dtype=torch.int32, device=dev), torch.arange(n, dtype=torch.int32, device=dev))
+
+
+def _block_gt(n: int, per: int, dev: torch.device):
+    return (torch.arange(0, per * n + 1, per, dtype=torch.int32, device=dev),
+            torch.arange(per * n, dtype=torch.int32, device=dev))
+
+
+# ------------------------------------------------------------------------------------------------ scoring
+def maxsim_scores_device(q_items: List[torch.Tensor], d_items: List[torch.Tensor], dev: torch.device) -> torch.Tensor:
+    q_flat, q_off, _ = _flatten(q_items, dev)
+    d_flat, d_off, d_lens = _flatten(d_items, dev)
+    flags = _pad_flags(d_lens)
+    d_zero = _np_h2d(flags, dev, torch.uint8) if flags.any() else None
+    return ops.maxsim_scores(q_flat, q_off, d_flat, d_off, d_zero)
+
+
+def compute_similarity_scores(img_embeds: Union[torch.Tensor, List[torch.Tensor]],
+                              txt_embeds: Union[torch.Tensor, List[torch.Tensor]],
+                              m_info: Dict, processor: Any = None) -> torch.Tensor:
+    """main.py:440-475. Returns fp32 scores [n_txt, n_img] on the CPU.
+
+    ColPali: txt_embeds are the MaxSim queries, img_embeds the documents (main.py:462-467); `processor` is unused —
+    its `.score` arithmetic (colpali_engine score_multi_vector, fp32 accumulate) runs in the K2 kernel.
+    Dense: txt.float() @ img.float().t() on tcgen05 (bf16 products are exact in fp32)."""
+    dev = _device()
+    if m_info["type"] == "colpali":
+        scores = maxsim_scores_device(_as_list(txt_embeds), _as_list(img_embeds), dev)
+    else:
+        Q = _h2d(_as_bf16(txt_embeds, "txt_embeds"), dev)
+        G = _h2d(_as_bf16(img_embeds, "img_embeds"), dev)
+        scores = ops.dense_scores(Q, G)
+    return scores.cpu()
+
+
+# ------------------------------------------------------------------------------------------------ metrics
+def _recall_block(scores: torch.Tensor, gt_sets: Sequence[Sequence[int]], dev: torch.device) -> ops.ProtocolRanks:
+    s = _h2d(scores if scores.dtype == torch.float32 else scores.float(), dev)
+    off, idx = _gt_dev(gt_sets, dev)
+    return ops.rank_from_scores(s, off, idx, want_bits=False)
+
+
+def compute_metrics_detailed(scores_t2i: torch.Tensor, scores_i2t: torch.Tensor, scores_i2t_symmetric: torch.Tensor,
+                             query_to_img: List[int], img_to_caps: Dict[int, List[int]],
+                             img_to_single_cap: Dict[int, int], captions: List[str]) -> Dict[str, Any]:
+    """main.py:305-383. Same nine ``{T2I,I2T,I2T_Sym}_R@{1,5,10}`` floats (= 100.0*correct/n) and the same
+    ``_query_results`` records; a query is correct at k iff fewer than k columns score strictly above its best
+    ground-truth column (identical to torch.topk membership outside exact fp32 ties)."""
+    dev = _device()
+    n_text = scores_t2i.size(0)
+    n_img = scores_i2t.size(0)
+    r_t2i = _recall_block(scores_t2i, [[query_to_img[i]] for i in range(n_text)], dev)
+    r_i2t = _recall_block(scores_i2t, [img_to_caps[i] for i in range(n_img)], dev)
+    r_sym = _recall_block(scores_i2t_symmetric, [[img_to_single_cap[i]] for i in range(n_img)], dev)
+    metrics: Dict[str, Any] = {}
+    for name, r in (("T2I", r_t2i), ("I2T", r_i2t), ("I2T_Sym", r_sym)):
+        for k, v in r.recall().items():
+            metrics[f"{name}_R@{k}"] = v
+    correct_r1 = (r_t2i.cnt_above < 1).cpu().tolist()
+    query_results = []
+    for i in range(n_text):                                       # main.py:342-356
+        caption = captions[i] if i < len(captions) else ""
+        cx = analyze_query_complexity(caption)
+        query_results.append({
+            "query_idx": i, "caption": caption, "correct_r1": bool(correct_r1[i]), "has_spatial": cx["has_spatial"],
+            "has_color": cx["has_color"], "has_counting": cx["has_counting"], "caption_length": cx["length"],
+            "category": get_category_from_caption(caption),
+        })
+    metrics["_query_results"] = query_results
+    return metrics
+
+
+def compute_metrics(scores_t2i: torch.Tensor, scores_i2t: torch.Tensor, query_to_img: List[int],
+                    img_to_caps: Dict[int, List[int]]) -> Dict[str, float]:
+    """run_benchmark_grand_slam_v28_publication_ready.py:203-229 (T2I + I2T, six keys)."""
+    dev = _device()
+    n_text, n_img = scores_t2i.size(0), scores_i2t.size(0)
+    r_t2i = _recall_block(scores_t2i, [[query_to_img[i]] for i in range(n_text)], dev)
+    r_i2t = _recall_block(scores_i2t, [img_to_caps[i] for i in range(n_img)], dev)
+    metrics: Dict[str, float] = {}
+    for name, r in (("T2I", r_t2i), ("I2T", r_i2t)):
+        for k, v in r.recall().items():
+            metrics[f"{name}_R@{k}"] = v
+    return metrics
+
+
+# ------------------------------------------------------------------------------------------------ statistics
+def _rng(rng):
+    return np.random if rng is None else rng
+
+
+def bootstrap_confidence_interval(data: np.ndarray, confidence: float = 0.95, rng=None) -> Tuple[float, float, float]:
+    """main.py:259-278. Consumes the same numpy stream as the reference's 10 000 ``np.random.choice(data, n)`` calls;
+    the 10 000 resample means are computed on the device in numpy's fp64 pairwise order, the two percentiles by
+    ``np.percentile`` itself on those identical values. Returns (mean, lower, upper)."""
+    dev = _device()
+    data = np.asarray(data)
+    n = len(data)
+    idx = _rng(rng).randint(0, n, size=(N_BOOTSTRAP, n))                     # == N_BOOTSTRAP x choice
+    d = _np_h2d(data.astype(np.float64, copy=False), dev, torch.float64)
+    means = ops.ci_means(d, _np_h2d(idx.astype(np.int32), dev, torch.int32)).cpu().numpy()
+    mean = np.mean(data)
+    alpha = (1 - confidence) / 2
+    lower = np.percentile(means, alpha * 100)
+    upper = np.percentile(means, (1 - alpha) * 100)
+    return mean, lower, upper
+
+
+def permutation_test(data1: np.ndarray, data2: np.ndarray, n_permutations: int = 10000, rng=None) -> float:
+    """main.py:281-302. The cumulative in-place shuffles of ``combined`` are replayed on an index array with the
+    same numpy stream; the 2 x n_permutations means and |diff| run on the device in numpy's summation order."""
+    dev = _device()
+    data1, data2 = np.asarray(data1, dtype=np.float64), np.asarray(data2, dtype=np.float64)
+    observed_diff = np.abs(np.mean(data1) - np.mean(data2))
+    combined = np.concatenate([data1, data2])
+    n1, n = len(data1), len(data1) + len(data2)
+    r = _rng(rng)
+    idx = np.arange(n, dtype=np.int64)
+    perm = np.empty((n_permutations, n), dtype=np.int32)
+    for p in range(n_permutations):
+        r.shuffle(idx)                                                       # main.py:296
+        perm[p] = idx
+    diffs = ops.perm_stats(_np_h2d(combined, dev, torch.float64), n1, _np_h2d(perm, dev, torch.int32)).cpu().numpy()
+    return np.mean(diffs >= observed_diff)
+
+
+# ------------------------------------------------------------------------------------------------ fused path
+def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, caps_per_img: int = 5,
+                   want_bits: bool = True) -> Dict[str, ops.ProtocolRanks]:
+    """One scoring pass over the BASE embeddings for the three protocols of run_bootstrap_benchmark
+    (main.py:599-624 GT structure: query i <-> image i, image i <-> captions [5i, 5i+5)).
+
+    Dense models never materialise a score matrix (K1). ColPali writes the final [n_q, n_doc] fp32 scores (one float
+    per 5.3 MFLOP pair) and ranks them with KR; I2T uses images as MaxSim queries (v28 :375-386) and I2T_Sym the
+    transposed T2I matrix exactly as main.py:624."""
+    dev = _device()
+    out: Dict[str, ops.ProtocolRanks] = {}
+    if m_info["type"] == "colpali":
+        img, t2i, allc = _as_list(img_embeds), _as_list(t2i_txt_embeds), _as_list(all_txt_embeds)
+        n = len(img)
+        i_flat, i_off, i_lens = _flatten(img, dev)
+        t_flat, t_off, t_lens = _flatten(t2i, dev)
+        a_flat, a_off, a_lens = _flatten(allc, dev)
+        fl_i, fl_a = _pad_flags(i_lens), _pad_flags(a_lens)
+        s_t2i = ops.maxsim_scores(t_flat, t_off, i_flat, i_off, _np_h2d(fl_i, dev, torch.uint8) if fl_i.any() else None)
+        s_i2t = ops.maxsim_scores(i_flat, i_off, a_flat, a_off, _np_h2d(fl_a, dev, torch.uint8) if fl_a.any() else None)
+        id_off, id_idx = _identity_gt(n, dev)
+        b_off, b_idx = _block_gt(n, caps_per_img, dev)
+        out["T2I"] = ops.rank_from_scores(s_t2i, id_off, id_idx, want_bits)
+        out["I2T"] = ops.rank_from_scores(s_i2t, b_off, b_idx, want_bits)
+        out["I2T_Sym"] = ops.rank_from_scores(s_t2i.t().contiguous(), id_off, id_idx, want_bits)
+    else:
+        img = _h2d(_as_bf16(img_embeds, "img_embeds"), dev)
+        t2i = _h2d(_as_bf16(t2i_txt_embeds, "t2i_txt_embeds"), dev)
+        allc = _h2d(_as_bf16(all_txt_embeds, "all_txt_embeds"), dev)
+        n = img.shape[0]
+        id_off, id_idx = _identity_gt(n, dev)
+        b_off, b_idx = _block_gt(n, caps_per_img, dev)
+        out["T2I"] = ops.dense_rank(t2i, img, id_off, id_idx, want_bits)         # [n_txt, n_img]   main.py:620
+        out["I2T"] = ops.dense_rank(img, allc, b_off, b_idx, want_bits)          # [n_img, 5 n_img] main.py:622 (D1 fixed)
+        out["I2T_Sym"] = ops.dense_rank(img, t2i, id_off, id_idx, want_bits)     # = scores_t2i.t() main.py:624
+    out["I2T"].col2unit = torch.arange(n * caps_per_img, dtype=torch.int32, device=dev) // caps_per_img
+    return out
+
+
+def base_metrics(ranks: Dict[str, ops.ProtocolRanks]) -> Dict[str, float]:
+    """The nine Recall@K values of the un-resampled pass, keyed like compute_metrics_detailed."""
+    m: Dict[str, float] = {}
+    for name in ("T2I", "I2T", "I2T_Sym"):
+        for k, v in ranks[name].recall().items():
+            m[f"{name}_R@{k}"] = v
+    return m
+
+
+def bootstrap_from_ranks(ranks: Dict[str, ops.ProtocolRanks], sample_indices: np.ndarray, n_images: int,
+                         want_hits: bool = False):
+    """K3: int64 [B, 9] correct counts (METRIC_KEYS order) for the reference's resample draws
+    ``sample_indices`` [B, N] (main.py:588), without rescoring. With want_hits also returns, per base T2I query,
+    (R@1 hits summed over iterations, times drawn) — the inputs of aggregate_failure_analysis."""
+    dev = _device()
+    si = _np_h2d(np.asarray(sample_indices).astype(np.int32), dev, torch.int32)
+    mult = ops.bincount(si, n_images)
+    cols = []
+    hits = torch.zeros(ranks["T2I"].nq, dtype=torch.int32, device=dev) if want_hits else None
+    for name in ("T2I", "I2T", "I2T_Sym"):
+        cols.append(ops.boot_counts(ranks[name], mult, q_hits1=hits if name == "T2I" else None))
+    correct = torch.cat(cols, dim=1).cpu().numpy().astype(np.int64)
+    if want_hits:
+        drawn = mult.sum(dim=0, dtype=torch.int64)
+        qu = ranks["T2I"].q_unit
+        drawn = drawn if qu is None else drawn[qu.long()]
+        return correct, hits.cpu().numpy().astype(np.int64), drawn.cpu().numpy()
+    return correct
+
+
+def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, n_iterations: int,
+                                  rng=None, t2i_captions: Optional[List[str]] = None, encoding_time: float = 0.0,
+                                  t_start: Optional[float] = None) -> Dict[str, Any]:
+    """Everything run_bootstrap_benchmark does after encoding (main.py:563-667) -> the 42-column row dict.
+
+    numpy stream consumption matches the reference: n_iterations x choice(N, N), then for each of the nine metric
+    keys in insertion order 10 000 x choice(values, n_iterations)."""
+    t0 = time.time() if t_start is None else t_start
+    n_images = len(img_embeds)
+    ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info)
+    sample_indices = _rng(rng).randint(0, n_images, size=(n_iterations, n_images))        # main.py:588
+    correct, hits, drawn = bootstrap_from_ranks(ranks, sample_indices, n_images, want_hits=True)
+    values = 100.0 * correct / n_images                                                    # main.py:358,368,378
+    torch.cuda.synchronize()
+    total_time = time.time() - t0                                                          # main.py:636
+    aggregated: Dict[str, Any] = {"Model": m_info["name"]}
+    for j, key in enumerate(METRIC_KEYS):                                                  # main.py:644-651
+        v = np.ascontiguousarray(values[:, j])
+        mean, lower, upper = bootstrap_confidence_interval(v, rng=rng)
+        aggregated[f"{key}_mean"] = mean
+        aggregated[f"{key}_lower"] = lower
+        aggregated[f"{key}_upper"] = upper
+        aggregated[f"{key}_std"] = np.std(v)
+    enc = encoding_time if encoding_time > 0 else float("nan")
+    aggregated["Time"] = total_time
+    aggregated["QPS"] = n_images / enc
+    aggregated["Encoding_Time"] = encoding_time
+    aggregated["Img_per_sec"] = n_images / enc
+    caps = t2i_captions if t2i_captions is not None else [""] * n_images
+    aggregated["_failure_analysis"] = aggregate_failure_from_hits(caps, hits, drawn)      # main.py:664
+    aggregated["_bootstrap_values"] = {k: values[:, j].copy() for j, k in enumerate(METRIC_KEYS)}
+    aggregated["_base_metrics"] = base_metrics(ranks)
+    return aggregated
+
+
+def run_bootstrap_benchmark(model, processor, m_info: Dict, dataset, n_iterations: int, *, encode_data=None,
+                            load_cached_image=None, get_all_captions=None) -> Dict[str, Any]:
+    """main.py:478-667. The dataset walk and the encoders stay upstream (out of scope): pass the reference's own
+    ``encode_data`` / ``load_cached_image`` / ``get_all_captions`` callables. Everything after the encoders runs on
+    the B200 path. Returns the row dict of main.py:643-665 ({} when no valid image, as the reference)."""
+    if encode_data is None or load_cached_image is None or get_all_captions is None:
+        raise TypeError("run_bootstrap_benchmark needs the upstream encode_data / load_cached_image / "
+                        "get_all_captions callables (the encoders are not part of this library)")
+    images, t2i_captions, all_captions = [], [], []
+    for item in dataset:                                                                   # main.py:508-525
+        img = load_cached_image(item)
+        if img is None:
+            continue
+        caps_raw = get_all_captions(item, "sentences")
+        if len(caps_raw) < 5:
+            continue
+        caps = caps_raw[:5]
+        images.append(img)
+        t2i_captions.append(caps[0])
+        all_captions.extend(caps)
+    if not images:
+        return {}
+    t_start = time.time()
+    img_embeds, _ = encode_data(model, processor, m_info, images, [])                      # main.py:551-557
+    _, t2i_txt_embeds = encode_data(model, processor, m_info, [], t2i_captions)
+    _, all_txt_embeds = encode_data(model, processor, m_info, [], all_captions)
+    encoding_time = time.time() - t_start
+    row = run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info, n_iterations,
+                                        t2i_captions=t2i_captions, encoding_time=encoding_time, t_start=t_start)
+    return {k: v for k, v in row.items() if k in CSV_COLUMNS}
+
+
+def write_results_csv(rows: List[Dict[str, Any]], path: str) -> None:
+    """main.py:834-837: pd.DataFrame(rows).to_csv(path, index=False) with the reference's 42 columns."""
+    import pandas as pd
+    pd.DataFrame([{k: r[k] for k in CSV_COLUMNS if k in r} for r in rows]).to_csv(path, index=False)

@@ -1,0 +1,323 @@
+// K1 — dense CLIP/SigLIP similarity as a tcgen05 GEMM whose epilogue ranks instead of storing.
+//
+//   S[q, g] = sum_k bf16(Q[q,k]) * bf16(G[g,k])   (fp32 accumulate in TMEM)
+//
+// Replaces torch.matmul(txt.float(), img.float().t()) at /root/reference/main.py:473 (v28 :390-391) together with
+// the per-row torch.topk membership tests of main.py:331-378: the 5k x 25k score matrix is never written.
+// Two passes over the same MMA code, so a ground-truth score is bit-identical in both and can never beat itself:
+//   MODE_THRESHOLD  only tiles that hold a GT column; epilogue: thr[q] = max(thr[q], S[q, c]) for c in GT(q)
+//   MODE_COUNT      every tile; epilogue: bits = (S[q, :] > thr[q]) packed 32 columns per word, cnt_above += popc,
+//                   optionally the fp32 scores themselves (the drop-in compute_similarity_scores needs them).
+//
+// CTA = persistent worker over 128 x 256 output tiles; K streams through a 4-stage TMA ring in 64-wide
+// (128-byte, swizzled) blocks; accumulators ping-pong between TMEM columns [0,256) and [256,512) so the epilogue
+// of tile t overlaps the MMAs of tile t+1. Warp roles: 0 = TMA, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+#include <cfloat>
+
+#include "../../include/mmx.h"
+#include "mmx_host.cuh"
+#include "sm100_ptx.cuh"
+
+namespace mmx {
+namespace dense {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int NSTAGE = 4;
+constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int NUM_THREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int BAND = 16;  // row tiles per raster band: concurrent CTAs share A and B tiles through L2
+
+struct Params {
+    const int32_t* gt_off;
+    const int32_t* gt_idx;
+    long long g_base;
+    float* thr;
+    int32_t* cnt_above;
+    uint32_t* above_bits;
+    long long words_per_row;
+    float* scores;
+    long long ld_scores;
+    const int32_t* tile_list;   // MODE_THRESHOLD: compacted ids of tiles holding a GT column
+    const int32_t* n_tiles_dev; // MODE_THRESHOLD: their count (device scalar)
+    long long nq, ng;
+    int kblocks, n_mblk, n_ntile, n_tiles, mode;
+};
+
+struct __align__(1024) Smem {
+    uint8_t stage[NSTAGE][STAGE_BYTES];
+    uint64_t full[NSTAGE], empty[NSTAGE];
+    uint64_t t_full[2], t_empty[2];
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, int& n_tile) {
+    const int per_band = BAND * p.n_ntile;
+    const int band = t / per_band;
+    const int rem = t - band * per_band;
+    const int rows = min(BAND, p.n_mblk - band * BAND);
+    n_tile = rem / rows;
+    m_blk = band * BAND + rem % rows;
+}
+__device__ __forceinline__ int tile_id(const Params& p, int i) {
+    return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i;
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.0f)
+        atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
+                  const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_g);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < NSTAGE; ++i) {
+            mbar_init(&s.full[i], 1);
+            mbar_init(&s.empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&s.t_full[i], 1);
+            mbar_init(&s.t_empty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&s.tmem_base, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_base;
+    const int n_work = p.n_tiles_dev != nullptr ? __ldg(p.n_tiles_dev) : p.n_tiles;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t kc = 0;
+            for (int i = blockIdx.x; i < n_work; i += gridDim.x) {
+                int m_blk, n_tile;
+                tile_coords(p, tile_id(p, i), m_blk, n_tile);
+                for (int kb = 0; kb < p.kblocks; ++kb, ++kc) {
+                    const uint32_t st = kc % NSTAGE, ph = (kc / NSTAGE) & 1;
+                    mbar_wait(&s.empty[st], ph ^ 1);
+                    mbar_arrive_expect_tx(&s.full[st], STAGE_BYTES);
+                    tma_load_2d(s.stage[st], &tmap_q, &s.full[st], kb * BK, m_blk * BM);
+                    tma_load_2d(s.stage[st] + A_BYTES, &tmap_g, &s.full[st], kb * BK, n_tile * BN);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+            uint32_t kc = 0, tc = 0;
+            for (int i = blockIdx.x; i < n_work; i += gridDim.x, ++tc) {
+                const uint32_t acc = tc & 1, use = tc >> 1;
+                mbar_wait(&s.t_empty[acc], (use & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < p.kblocks; ++kb, ++kc) {
+                    const uint32_t st = kc % NSTAGE, ph = (kc / NSTAGE) & 1;
+                    mbar_wait(&s.full[st], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(s.stage[st]);
+                    const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_ss(tmem_base + acc * BN, umma_desc_kmajor_sw128(a_addr + k * 32),
+                                     umma_desc_kmajor_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    umma_commit(&s.empty[st]);
+                }
+                umma_commit(&s.t_full[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int wq = warp & 3;
+        const int row = wq * 32 + lane;
+        uint32_t tc = 0;
+        for (int i = blockIdx.x; i < n_work; i += gridDim.x, ++tc) {
+            int m_blk, n_tile;
+            tile_coords(p, tile_id(p, i), m_blk, n_tile);
+            const uint32_t acc = tc & 1, use = tc >> 1;
+            const long long q = (long long)m_blk * BM + row;
+            const long long n0 = (long long)n_tile * BN;
+            const bool valid_row = q < p.nq;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
+            // per-row state, loaded while the MMAs of this tile are still running
+            float thr = INFINITY;
+            int e0 = 0, e1 = 0;
+            if (p.mode == MMX_MODE_COUNT) {
+                if (valid_row) thr = __ldg(p.thr + q);
+            } else if (valid_row) {
+                e0 = __ldg(p.gt_off + q);
+                e1 = __ldg(p.gt_off + q + 1);
+            }
+            mbar_wait(&s.t_full[acc], use & 1);
+            tc_fence_after();
+            int cnt = 0;
+            float best = -INFINITY;
+#pragma unroll 1
+            for (int ch = 0; ch < BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + ch * 32, v);
+                tmem_ld_wait();
+                const long long c0 = n0 + ch * 32;
+                if (p.mode == MMX_MODE_COUNT) {
+                    const long long nvalid = p.ng - c0;
+                    const uint32_t cmask = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << (int)nvalid) - 1u));
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
+                    bits &= cmask;
+                    cnt += __popc(bits);
+                    const long long w = (c0 >> 5);
+                    if (p.above_bits != nullptr && valid_row && w < p.words_per_row)
+                        p.above_bits[q * p.words_per_row + w] = bits;
+                    if (p.scores != nullptr && valid_row) {
+                        float* dst = p.scores + q * p.ld_scores + c0;
+                        if (nvalid >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) =
+                                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j < nvalid) dst[j] = __uint_as_float(v[j]);
+                        }
+                    }
+                } else {
+                    for (int e = e0; e < e1; ++e) {
+                        const long long lc = (long long)__ldg(p.gt_idx + e) - p.g_base - c0;
+                        if (lc >= 0 && lc < 32 && lc + c0 < p.ng) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (j == (int)lc) best = fmaxf(best, __uint_as_float(v[j]));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.t_empty[acc]);
+            if (p.mode == MMX_MODE_COUNT) {
+                if (valid_row && cnt > 0) atomicAdd(p.cnt_above + q, cnt);
+            } else if (valid_row && best > -INFINITY) {
+                atomic_max_float(p.thr + q, best);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// MODE_THRESHOLD work list: ids of the (row tile, column tile) pairs that contain at least one GT column.
+__global__ void gt_tiles_kernel(const int32_t* __restrict__ gt_off, const int32_t* __restrict__ gt_idx, long long nq,
+                                long long ng, long long g_base, int n_mblk, int n_ntile, int32_t* __restrict__ flags,
+                                int32_t* __restrict__ list, int32_t* __restrict__ count) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int m_blk = (int)(q / BM);
+    const int band = m_blk / BAND;
+    const int rows = min(BAND, n_mblk - band * BAND);
+    for (int e = gt_off[q]; e < gt_off[q + 1]; ++e) {
+        const long long c = (long long)gt_idx[e] - g_base;
+        if (c < 0 || c >= ng) continue;
+        const int n_tile = (int)(c / BN);
+        const int t = band * BAND * n_ntile + n_tile * rows + (m_blk - band * BAND);
+        if (atomicExch(&flags[t], 1) == 0) list[atomicAdd(count, 1)] = t;
+    }
+}
+
+}  // namespace dense
+}  // namespace mmx
+
+using namespace mmx;
+using namespace mmx::dense;
+
+extern "C" int mmx_dense_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes) {
+    MMX_REQUIRE(bytes != nullptr, "bytes == NULL");
+    const int64_t tiles = ((nq + BM - 1) / BM) * ((ng + BN - 1) / BN);
+    *bytes = (size_t)tiles * 8 + 512;
+    return 0;
+}
+
+extern "C" int mmx_dense_rank(const void* Q, int64_t nq, const void* G, int64_t ng, int d, const int32_t* gt_off,
+                              const int32_t* gt_idx, int64_t g_base, int mode, float* thr, int32_t* cnt_above,
+                              uint32_t* above_bits, int64_t words_per_row, float* scores, int64_t ld_scores,
+                              void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    MMX_REQUIRE(nq >= 0 && ng >= 0 && d >= 8 && d % 8 == 0, "bad shape nq=%lld ng=%lld d=%d (d must be a multiple of 8)",
+                (long long)nq, (long long)ng, d);
+    MMX_REQUIRE(mode == MMX_MODE_THRESHOLD || mode == MMX_MODE_COUNT, "unknown mode %d", mode);
+    MMX_REQUIRE(thr != nullptr, "thr == NULL");
+    if (nq == 0 || ng == 0) return 0;
+    if (mmx_device_check() != 0) return -3;
+    const long long n_mblk = (nq + BM - 1) / BM, n_ntile = (ng + BN - 1) / BN;
+    MMX_REQUIRE(n_mblk * n_ntile < (1ll << 31), "too many tiles");
+    Params p;
+    p.gt_off = gt_off;
+    p.gt_idx = gt_idx;
+    p.g_base = g_base;
+    p.thr = thr;
+    p.cnt_above = cnt_above;
+    p.above_bits = above_bits;
+    p.words_per_row = words_per_row;
+    p.scores = scores;
+    p.ld_scores = ld_scores;
+    p.tile_list = nullptr;
+    p.n_tiles_dev = nullptr;
+    p.nq = nq;
+    p.ng = ng;
+    p.kblocks = (d + BK - 1) / BK;
+    p.n_mblk = (int)n_mblk;
+    p.n_ntile = (int)n_ntile;
+    p.n_tiles = (int)(n_mblk * n_ntile);
+    p.mode = mode;
+    if (mode == MMX_MODE_COUNT) {
+        MMX_REQUIRE(cnt_above != nullptr, "cnt_above == NULL");
+        MMX_REQUIRE(above_bits == nullptr || words_per_row >= (ng + 31) / 32, "words_per_row too small");
+        MMX_REQUIRE(scores == nullptr || ld_scores >= ng, "ld_scores < ng");
+    } else {
+        MMX_REQUIRE(gt_off != nullptr && gt_idx != nullptr, "GT CSR missing");
+        size_t need = 0;
+        mmx_dense_workspace_bytes(nq, ng, &need);
+        MMX_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: need %zu bytes", need);
+        uintptr_t ws = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
+        int32_t* count = reinterpret_cast<int32_t*>(ws);
+        int32_t* flags = count + 64;
+        int32_t* list = flags + p.n_tiles;
+        MMX_CHECK_CUDA(cudaMemsetAsync(count, 0, (size_t)(64 + p.n_tiles) * 4, stream));
+        gt_tiles_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(gt_off, gt_idx, nq, ng, g_base, p.n_mblk,
+                                                                          p.n_ntile, flags, list, count);
+        MMX_CHECK_CUDA(cudaGetLastError());
+        p.tile_list = list;
+        p.n_tiles_dev = count;
+    }
+    CUtensorMap tq, tg;
+    if (make_tmap_bf16_sw128(&tq, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, BM) != 0) return -4;
+    if (make_tmap_bf16_sw128(&tg, G, (uint64_t)ng, (uint64_t)d, (uint64_t)d, BN) != 0) return -4;
+    const size_t smem_bytes = sizeof(Smem) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attr_set = true;
+    }
+    const int sms = sm_count();
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    dense_rank_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

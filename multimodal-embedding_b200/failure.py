@@ -1,0 +1,124 @@
+"""Failure-analysis consumer of the hot path: caption keyword features + accuracy breakdowns.
+
+Host-side string/dict work exactly like the reference (main.py:102-125 keyword tables, :239-256 feature helpers,
+:669-722 aggregation). The only input that comes from the GPU path is each query's ``correct_r1`` bit; for the
+bootstrap the per-query hit totals come from K3 (``q_hits1``) instead of 5 000 000 per-iteration dict records.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Any, Dict, List, Optional, Sequence
+
+import numpy as np
+
+COCO_SUPERCATEGORIES = {   # main.py:102-118
+    "person": ["person"],
+    "vehicle": ["bicycle", "car", "motorcycle", "airplane", "bus", "train", "truck", "boat"],
+    "outdoor": ["traffic light", "fire hydrant", "stop sign", "parking meter", "bench"],
+    "animal": ["bird", "cat", "dog", "horse", "sheep", "cow", "elephant", "bear", "zebra", "giraffe"],
+    "accessory": ["backpack", "umbrella", "handbag", "tie", "suitcase"],
+    "sports": ["frisbee", "skis", "snowboard", "sports ball", "kite", "baseball bat", "baseball glove", "skateboard",
+               "surfboard", "tennis racket"],
+    "kitchen": ["bottle", "wine glass", "cup", "fork", "knife", "spoon", "bowl"],
+    "food": ["banana", "apple", "sandwich", "orange", "broccoli", "carrot", "hot dog", "pizza", "donut", "cake"],
+    "furniture": ["chair", "couch", "potted plant", "bed", "dining table", "toilet"],
+    "electronic": ["tv", "laptop", "mouse", "remote", "keyboard", "cell phone"],
+    "appliance": ["microwave", "oven", "toaster", "sink", "refrigerator"],
+    "indoor": ["book", "clock", "vase", "scissors", "teddy bear", "hair drier", "toothbrush"],
+}
+SPATIAL_KEYWORDS = ["left", "right", "top", "bottom", "above", "below", "next to", "beside", "in front", "behind",
+                    "between", "near", "far"]                                                       # main.py:121-122
+COLOR_KEYWORDS = ["red", "blue", "green", "yellow", "black", "white", "orange", "purple", "pink", "brown", "gray",
+                  "grey"]                                                                           # main.py:123-124
+COUNTING_KEYWORDS = ["one", "two", "three", "four", "five", "1", "2", "3", "4", "5", "single", "double", "triple",
+                     "multiple", "several", "many", "few"]                                          # main.py:125-126
+LENGTH_BINS = [(0, 5), (6, 10), (11, 15), (16, 100)]                                                # main.py:714
+FEATURES = ["has_spatial", "has_color", "has_counting"]
+
+
+def analyze_query_complexity(caption: str) -> Dict[str, Any]:
+    """main.py:239-247."""
+    text = caption.lower()
+    return {
+        "has_spatial": any(kw in text for kw in SPATIAL_KEYWORDS),
+        "has_color": any(kw in text for kw in COLOR_KEYWORDS),
+        "has_counting": any(kw in text for kw in COUNTING_KEYWORDS),
+        "length": len(caption.split()),
+    }
+
+
+def get_category_from_caption(caption: str) -> Optional[str]:
+    """main.py:249-256: first supercategory (table order) with a keyword contained in the caption."""
+    text = caption.lower()
+    for name, keywords in COCO_SUPERCATEGORIES.items():
+        if any(kw in text for kw in keywords):
+            return name
+    return None
+
+
+def _pct(hits: int, total: int) -> float:
+    return 100.0 * hits / total
+
+
+def aggregate_failure_from_hits(captions: Sequence[str], hits: np.ndarray, drawn: np.ndarray,
+                                first_seen_order: Optional[Sequence[int]] = None) -> Dict[str, Any]:
+    """main.py:669-722 evaluated from per-BASE-query totals: ``hits[q]`` = number of (iteration, copy) records of
+    query q with correct_r1, ``drawn[q]`` = number of records of query q. Caption features are computed once per base
+    caption. ``first_seen_order`` (query indices in the order the reference's flattened record list first meets them)
+    only fixes the insertion order of ``accuracy_by_category``; default = query order."""
+    hits = np.asarray(hits, dtype=np.int64)
+    drawn = np.asarray(drawn, dtype=np.int64)
+    total = int(drawn.sum())
+    if total == 0:
+        return {}
+    feats = [analyze_query_complexity(c) for c in captions]
+    cats = [get_category_from_caption(c) for c in captions]
+    analysis: Dict[str, Any] = {"overall_accuracy": _pct(int(hits.sum()), total)}
+    for f in FEATURES:
+        mask = np.array([bool(x[f]) for x in feats], dtype=bool)
+        if drawn[mask].sum() > 0:
+            analysis[f"accuracy_{f}"] = _pct(int(hits[mask].sum()), int(drawn[mask].sum()))
+        if drawn[~mask].sum() > 0:
+            analysis[f"accuracy_not_{f}"] = _pct(int(hits[~mask].sum()), int(drawn[~mask].sum()))
+    order = range(len(captions)) if first_seen_order is None else first_seen_order
+    by_cat_h: Dict[str, int] = {}
+    by_cat_n: Dict[str, int] = defaultdict(int)
+    for q in order:
+        c = cats[q]
+        if c and drawn[q] > 0 and c not in by_cat_h:
+            by_cat_h[c] = 0
+    for q, c in enumerate(cats):
+        if c and drawn[q] > 0:
+            by_cat_h[c] = by_cat_h.get(c, 0) + int(hits[q])
+            by_cat_n[c] += int(drawn[q])
+    analysis["accuracy_by_category"] = {c: _pct(h, by_cat_n[c]) for c, h in by_cat_h.items()}
+    lengths = np.array([x["length"] for x in feats], dtype=np.int64)
+    for lo, hi in LENGTH_BINS:
+        mask = (lengths >= lo) & (lengths <= hi)
+        if drawn[mask].sum() > 0:
+            analysis[f"accuracy_length_{lo}_{hi}"] = _pct(int(hits[mask].sum()), int(drawn[mask].sum()))
+    return analysis
+
+
+def aggregate_failure_analysis(all_query_results: List[List[Dict]]) -> Dict[str, Any]:
+    """main.py:669-722 on the reference's own record lists (what compute_metrics_detailed's ``_query_results`` feed)."""
+    flat = [r for it in all_query_results for r in it]
+    if not flat:
+        return {}
+    key_of: Dict[Any, int] = {}
+    caps: List[str] = []
+    hits: List[int] = []
+    drawn: List[int] = []
+    order: List[int] = []
+    for r in flat:
+        k = r["caption"]
+        if k not in key_of:
+            key_of[k] = len(caps)
+            caps.append(k)
+            hits.append(0)
+            drawn.append(0)
+            order.append(key_of[k])
+        i = key_of[k]
+        hits[i] += int(bool(r["correct_r1"]))
+        drawn[i] += 1
+    return aggregate_failure_from_hits(caps, np.array(hits), np.array(drawn), order)

@@ -1,0 +1,225 @@
+"""Device-level wrappers: one Python function per libmmx entry point, taking CUDA tensors.
+
+torch is plumbing here (device memory, streams); all arithmetic happens inside libmmx.so. Every wrapper raises when
+the library or a CUDA device is missing — there is no eager/CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MODE_THRESHOLD, MODE_COUNT = 0, 1
+LIST_LEN = 32          # entries kept per above-GT list (rows with more fall back to the exact bitmask walk)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*ts: torch.Tensor) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MmxError("libmmx operates on CUDA tensors only (no CPU fallback)")
+
+
+def csr_from_sets(gt_sets: Sequence[Sequence[int]]) -> Tuple[np.ndarray, np.ndarray]:
+    """Ground-truth sets -> CSR (int32 offsets [n+1], int32 indices)."""
+    off = np.zeros(len(gt_sets) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(g) for g in gt_sets])
+    idx = np.fromiter((int(c) for g in gt_sets for c in g), dtype=np.int32, count=int(off[-1]))
+    return off, idx
+
+
+@dataclass
+class ProtocolRanks:
+    """Result of one scoring pass for one protocol, resident on the device.
+
+    thr [nq] fp32 GT threshold, cnt_above [nq] int32 strict-greater count (= rank-1 of the best GT item),
+    bits [nq, wpr] uint32-as-int32 above-GT bitmask over gallery columns, col2unit / q_unit map columns / queries to
+    bootstrap units (images); None = identity."""
+    thr: torch.Tensor
+    cnt_above: torch.Tensor
+    bits: Optional[torch.Tensor]
+    n_cols: int
+    col2unit: Optional[torch.Tensor] = None
+    q_unit: Optional[torch.Tensor] = None
+    scores: Optional[torch.Tensor] = None
+
+    @property
+    def nq(self) -> int:
+        return int(self.cnt_above.shape[0])
+
+    def recall(self) -> dict:
+        """100.0 * correct / n exactly as main.py:358 (python float arithmetic on integer counts)."""
+        cnt = self.cnt_above
+        n = self.nq
+        ks = torch.tensor([1, 5, 10], device=cnt.device)
+        correct = (cnt[None, :] < ks[:, None]).sum(dim=1).tolist()
+        return {k: 100.0 * c / n for k, c in zip((1, 5, 10), correct)}
+
+
+def maxsim_scores(q_tok: torch.Tensor, q_off: torch.Tensor, d_tok: torch.Tensor, d_off: torch.Tensor,
+                  d_zero: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K2. q_tok [n_qtok,128] / d_tok [n_dtok,128] bf16 CUDA, offsets int32 CUDA -> fp32 [nq, nd] CUDA."""
+    _need_cuda(q_tok, q_off, d_tok, d_off, d_zero)
+    if q_tok.dtype != torch.bfloat16 or d_tok.dtype != torch.bfloat16:
+        raise TypeError("MaxSim kernel takes bf16 token embeddings")
+    q_tok, d_tok = q_tok.contiguous(), d_tok.contiguous()
+    nq, nd = q_off.numel() - 1, d_off.numel() - 1
+    if out is None:
+        out = torch.empty((nq, nd), dtype=torch.float32, device=q_tok.device)
+    need = ctypes.c_size_t()
+    h = _lib.lib()
+    _lib.check(h.mmx_maxsim_workspace_bytes(q_tok.shape[0], nd, ctypes.byref(need)))
+    ws = torch.empty(need.value, dtype=torch.uint8, device=q_tok.device)
+    _lib.check(h.mmx_maxsim_scores(q_tok.data_ptr(), q_off.data_ptr(), nq, q_tok.shape[0], d_tok.data_ptr(),
+                                   d_off.data_ptr(), nd, d_tok.shape[0], q_tok.shape[1] if q_tok.dim() == 2 else 0,
+                                   _ptr(d_zero), out.data_ptr(), out.stride(0), ws.data_ptr(), need.value, _stream()))
+    return out
+
+
+def _alloc_rank(nq: int, n_cols: int, device, want_bits: bool):
+    thr = torch.full((nq,), float("-inf"), dtype=torch.float32, device=device)
+    cnt = torch.zeros((nq,), dtype=torch.int32, device=device)
+    wpr = (n_cols + 31) // 32
+    bits = torch.empty((nq, wpr), dtype=torch.int32, device=device) if want_bits else None
+    return thr, cnt, bits, wpr
+
+
+def dense_rank(Q: torch.Tensor, G: torch.Tensor, gt_off: torch.Tensor, gt_idx: torch.Tensor, want_bits: bool = True,
+               want_scores: bool = False, g_base: int = 0, thr: Optional[torch.Tensor] = None,
+               threshold_only: bool = False) -> ProtocolRanks:
+    """K1. Q [nq,d], G [ng,d] bf16 CUDA; GT CSR int32 CUDA (global column ids) -> thresholds, counts, bitmask.
+
+    With `thr` given the threshold pass is skipped (multi-GPU: thresholds were max-reduced over shards first);
+    `threshold_only` stops after the threshold pass."""
+    _need_cuda(Q, G, gt_off, gt_idx, thr)
+    if Q.dtype != torch.bfloat16 or G.dtype != torch.bfloat16:
+        raise TypeError("dense rank kernel takes bf16 embeddings")
+    Q, G = Q.contiguous(), G.contiguous()
+    nq, d = Q.shape
+    ng = G.shape[0]
+    h = _lib.lib()
+    thr0, cnt, bits, wpr = _alloc_rank(nq, ng, Q.device, want_bits and not threshold_only)
+    scores = torch.empty((nq, ng), dtype=torch.float32, device=Q.device) if want_scores else None
+    if thr is None:
+        thr = thr0
+        need = ctypes.c_size_t()
+        _lib.check(h.mmx_dense_workspace_bytes(nq, ng, ctypes.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=Q.device)
+        _lib.check(h.mmx_dense_rank(Q.data_ptr(), nq, G.data_ptr(), ng, d, gt_off.data_ptr(), gt_idx.data_ptr(), g_base,
+                                    MODE_THRESHOLD, thr.data_ptr(), None, None, 0, None, 0, ws.data_ptr(), need.value,
+                                    _stream()))
+    if not threshold_only:
+        _lib.check(h.mmx_dense_rank(Q.data_ptr(), nq, G.data_ptr(), ng, d, gt_off.data_ptr(), gt_idx.data_ptr(), g_base,
+                                    MODE_COUNT, thr.data_ptr(), cnt.data_ptr(), _ptr(bits), wpr, _ptr(scores),
+                                    ng if want_scores else 0, None, 0, _stream()))
+    return ProtocolRanks(thr=thr, cnt_above=cnt, bits=bits, n_cols=ng, scores=scores)
+
+
+def dense_scores(Q: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
+    """K1 with the score output switched on and ranking neutralised (thr = +inf): fp32 CUDA [nq, ng] = Q @ G^T."""
+    _need_cuda(Q, G)
+    if Q.dtype != torch.bfloat16 or G.dtype != torch.bfloat16:
+        raise TypeError("dense score kernel takes bf16 embeddings")
+    Q, G = Q.contiguous(), G.contiguous()
+    nq, d = Q.shape
+    ng = G.shape[0]
+    thr = torch.full((nq,), float("inf"), dtype=torch.float32, device=Q.device)
+    cnt = torch.zeros((nq,), dtype=torch.int32, device=Q.device)
+    scores = torch.empty((nq, ng), dtype=torch.float32, device=Q.device)
+    _lib.check(_lib.lib().mmx_dense_rank(Q.data_ptr(), nq, G.data_ptr(), ng, d, None, None, 0, MODE_COUNT,
+                                         thr.data_ptr(), cnt.data_ptr(), None, 0, scores.data_ptr(), ng, None, 0,
+                                         _stream()))
+    return scores
+
+
+def rank_from_scores(scores: torch.Tensor, gt_off: torch.Tensor, gt_idx: torch.Tensor, want_bits: bool = True,
+                     g_base: int = 0, thr: Optional[torch.Tensor] = None, threshold_only: bool = False) -> ProtocolRanks:
+    """KR. fp32 CUDA score matrix [nq, ng] (any row pitch, unit column stride) -> thresholds, counts, bitmask."""
+    _need_cuda(scores, gt_off, gt_idx, thr)
+    if scores.dtype != torch.float32:
+        raise TypeError("rank_from_scores takes fp32 scores")
+    if scores.dim() != 2 or (scores.shape[1] > 1 and scores.stride(1) != 1):
+        scores = scores.contiguous()
+    nq, ng = scores.shape
+    ld = scores.stride(0) if nq > 1 else max(ng, 1)
+    h = _lib.lib()
+    thr0, cnt, bits, wpr = _alloc_rank(nq, ng, scores.device, want_bits and not threshold_only)
+    if thr is None:
+        thr = thr0
+        _lib.check(h.mmx_rank_from_scores(scores.data_ptr(), nq, ng, ld, gt_off.data_ptr(), gt_idx.data_ptr(), g_base,
+                                          MODE_THRESHOLD, thr.data_ptr(), None, None, 0, _stream()))
+    if not threshold_only:
+        _lib.check(h.mmx_rank_from_scores(scores.data_ptr(), nq, ng, ld, gt_off.data_ptr(), gt_idx.data_ptr(), g_base,
+                                          MODE_COUNT, thr.data_ptr(), cnt.data_ptr(), _ptr(bits), wpr, _stream()))
+    return ProtocolRanks(thr=thr, cnt_above=cnt, bits=bits, n_cols=ng)
+
+
+def bincount(sample_idx: torch.Tensor, n_units: int) -> torch.Tensor:
+    """int32 CUDA [B, n_draws] -> uint8 CUDA [B, n_units] multiplicities (saturated at 255)."""
+    _need_cuda(sample_idx)
+    if sample_idx.dtype != torch.int32:
+        raise TypeError("sample indices must be int32 on the device")
+    sample_idx = sample_idx.contiguous()
+    B, n_draws = sample_idx.shape
+    scratch = torch.empty((B, n_units), dtype=torch.int32, device=sample_idx.device)
+    mult = torch.empty((B, n_units), dtype=torch.uint8, device=sample_idx.device)
+    _lib.check(_lib.lib().mmx_bincount(sample_idx.data_ptr(), B, n_draws, n_units, scratch.data_ptr(), mult.data_ptr(),
+                                       _stream()))
+    return mult
+
+
+def boot_counts(r: ProtocolRanks, mult: torch.Tensor, list_len: int = LIST_LEN,
+                q_hits1: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """K3 for one protocol: mult uint8 CUDA [B, n_units] -> int32 CUDA [B, 3] correct counts for k = 1, 5, 10."""
+    _need_cuda(mult, r.bits)
+    if r.bits is None:
+        raise ValueError("bootstrap needs the above-GT bitmask (want_bits=True)")
+    B, n_units = mult.shape
+    nq, wpr = r.bits.shape
+    h = _lib.lib()
+    list_t = torch.empty((list_len, nq), dtype=torch.int32, device=mult.device)
+    _lib.check(h.mmx_above_lists(r.bits.data_ptr(), nq, wpr, _ptr(r.col2unit), list_len, list_t.data_ptr(), _stream()))
+    correct = torch.empty((B, 3), dtype=torch.int32, device=mult.device)
+    _lib.check(h.mmx_boot_counts(list_t.data_ptr(), list_len, r.cnt_above.data_ptr(), r.bits.data_ptr(), wpr,
+                                 _ptr(r.col2unit), _ptr(r.q_unit), mult.data_ptr(), B, n_units, nq, correct.data_ptr(),
+                                 _ptr(q_hits1), _stream()))
+    return correct
+
+
+def ci_means(data: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """K4. data fp64 CUDA [n], idx int32 CUDA [R, n] -> fp64 CUDA [R] = np.mean(data[idx[r]]) bit for bit."""
+    _need_cuda(data, idx)
+    if data.dtype != torch.float64 or idx.dtype != torch.int32:
+        raise TypeError("ci_means takes fp64 data and int32 indices")
+    data, idx = data.contiguous(), idx.contiguous()
+    R, n = idx.shape
+    if n != data.numel():
+        raise ValueError("idx rows must have len(data) entries")
+    out = torch.empty((R,), dtype=torch.float64, device=data.device)
+    _lib.check(_lib.lib().mmx_ci_means(data.data_ptr(), n, idx.data_ptr(), R, out.data_ptr(), _stream()))
+    return out
+
+
+def perm_stats(combined: torch.Tensor, n1: int, perm: torch.Tensor) -> torch.Tensor:
+    """K5. combined fp64 CUDA [n1+n2], perm int32 CUDA [P, n1+n2] -> fp64 CUDA [P] |mean(first n1) - mean(rest)|."""
+    _need_cuda(combined, perm)
+    if combined.dtype != torch.float64 or perm.dtype != torch.int32:
+        raise TypeError("perm_stats takes fp64 data and int32 permutations")
+    combined, perm = combined.contiguous(), perm.contiguous()
+    P, n = perm.shape
+    if n != combined.numel():
+        raise ValueError("perm rows must have len(combined) entries")
+    out = torch.empty((P,), dtype=torch.float64, device=combined.device)
+    _lib.check(_lib.lib().mmx_perm_stats(combined.data_ptr(), n1, n - n1, perm.data_ptr(), P, out.data_ptr(), _stream()))
+    return out

@@ -1,0 +1,55 @@
+"""Gallery/document sharding across the GPUs of one box: one process per GPU, queries replicated,
+gallery columns split into contiguous shards, exactly two tiny collectives per scoring pass:
+
+  1. all-reduce(MAX) of the per-query GT thresholds (the GT column of a query lives on one shard only);
+  2. all-reduce(SUM) of the strict-greater counts + all-gather of each shard's bitmask columns.
+
+Counts and bit columns are additive / concatenable over gallery shards, so the merged structures are bit-identical
+to an unsharded pass (tests/test_gpu_parity.py::test_dense_arbitrary_gt_and_sharded_gallery checks the arithmetic,
+tests/test_sharded_gloo.py the collectives with world_size 2 on CPU). The functions below only move tensors: they
+work on any torch.distributed backend (nccl on the B200s, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .ops import ProtocolRanks
+
+SHARD_ALIGN = 32   # shard boundaries fall on bitmask word boundaries
+
+
+def shard_bounds(n_cols: int, world: int, align: int = SHARD_ALIGN) -> List[Tuple[int, int]]:
+    """Contiguous [begin, end) column ranges, every boundary except the last a multiple of `align`."""
+    per = -(-n_cols // world)
+    per = -(-per // align) * align
+    return [(min(r * per, n_cols), min((r + 1) * per, n_cols)) for r in range(world)]
+
+
+def merge_thresholds(thr: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place max over ranks (a shard without the GT column contributes -inf)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(thr, op=dist.ReduceOp.MAX, group=group)
+    return thr
+
+
+def merge_ranks(local: ProtocolRanks, bounds: List[Tuple[int, int]], group=None) -> ProtocolRanks:
+    """Sum the counts, concatenate the bit columns of all shards (same result on every rank)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    cnt = local.cnt_above.clone()
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    bits = None
+    if local.bits is not None:
+        nq = local.bits.shape[0]
+        wmax = max((e - b + 31) // 32 for b, e in bounds)
+        mine = torch.zeros((nq, wmax), dtype=local.bits.dtype, device=local.bits.device)
+        mine[:, : local.bits.shape[1]] = local.bits
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        bits = torch.cat([p[:, : (e - b + 31) // 32] for p, (b, e) in zip(parts, bounds)], dim=1).contiguous()
+    return ProtocolRanks(thr=local.thr, cnt_above=cnt, bits=bits, n_cols=bounds[-1][1], col2unit=local.col2unit,
+                         q_unit=local.q_unit)

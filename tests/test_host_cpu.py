@@ -1,0 +1,67 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol (no compute calls),
+the failure-analysis mirror matches the reference's golden output, schema constants, padding flags, loud failure
+without a GPU."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import mmx
+import oracle
+from helpers import from_bits
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = mmx.build()
+    assert path.exists()
+    h = mmx._lib.lib()
+    declared = mmx._lib.declared_symbols()
+    assert len(declared) >= 13
+    missing = [s for s in declared if not hasattr(h, s)]
+    assert missing == []
+    assert h.mmx_abi_version() == 1
+    assert set(declared) <= set(mmx._lib._SIGNATURES) | {"mmx_last_error"}
+
+
+def test_csv_schema_matches_reference_order():
+    assert mmx.CSV_COLUMNS == oracle.CSV_COLUMNS
+    assert len(mmx.CSV_COLUMNS) == 42
+    assert mmx.METRIC_KEYS == oracle.METRIC_KEYS
+
+
+def test_failure_analysis_matches_reference_golden(golden_dir):
+    z = np.load(golden_dir / "dense.npz")
+    caps = [str(c) for c in z["captions"]]
+    hits = z["correct_r1"].astype(np.int64)
+    got = mmx.failure.aggregate_failure_from_hits(caps, hits, np.ones(len(caps), dtype=np.int64))
+    want = json.loads((golden_dir / "failure_analysis.json").read_text())
+    assert json.loads(json.dumps(got, sort_keys=True)) == want
+    recs = [{"caption": c, "correct_r1": bool(h)} for c, h in zip(caps, hits)]
+    got2 = mmx.aggregate_failure_analysis([recs[:20], recs[20:]])
+    assert json.loads(json.dumps(got2, sort_keys=True)) == want
+    for c in caps[:5]:
+        assert mmx.analyze_query_complexity(c) == oracle.metrics.analyze_query_complexity(c)
+        assert mmx.get_category_from_caption(c) == oracle.metrics.get_category_from_caption(c)
+
+
+def test_pad_flags_and_flatten():
+    lens = np.array([3, 3, 5, 1, 1, 1, 1, 1, 1, 1, 7, 7])
+    assert list(mmx.api._pad_flags(lens)) == list(oracle.maxsim_pad_flags(lens))
+    assert list(mmx.api._pad_flags(lens)) == [1, 1, 0, 1, 1, 1, 1, 1, 1, 1, 0, 0]
+
+
+def test_csr_from_sets():
+    off, idx = mmx.ops.csr_from_sets([[3], [], [1, 2]])
+    assert off.tolist() == [0, 1, 1, 3] and idx.tolist() == [3, 1, 2]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the loud failure on a GPU-less host")
+def test_no_cpu_fallback():
+    img = torch.zeros(4, 64, dtype=torch.bfloat16)
+    with pytest.raises(mmx.MmxError):
+        mmx.compute_similarity_scores(img, img, {"type": "dense"}, None)
+    with pytest.raises(mmx.MmxError):
+        mmx.bootstrap_confidence_interval(np.arange(10.0))
+    with pytest.raises(mmx.MmxError):
+        mmx.ops.dense_scores(img, img)
