@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py — the retrieval-scoring hot path on B200, measured against its roofline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
+
+Headline metric (BASELINE.json): MaxSim query-doc pairs/s on the ColPali-v1.3 configuration
+(25 000 queries x 20 tokens vs 5 000 docs x 1030 patches, 128-d bf16), one "step" = score every pair (K2) + rank
+(KR) + 1000-iteration bootstrap (K3) + the three CI resample-mean sets (K4). The second half of the metric — the
+5k x 25k dense score+rank+bootstrap wall-time (SigLIP-400M shapes, configs[1]) — is measured on rank 0 and carried in
+the same JSON line under "dense". Synthetic embeddings, seeded; no network, no checkpoints.
+
+  value     pairs/s with every input already resident in HBM (CUDA-event timed, max over ranks)
+  e2e       the same step through the public API (mmx.run_retrieval_bootstrap) from pinned HOST buffers: H2D of
+            the embeddings, the reference's numpy random draws on the host, D2H of the result — wall clock
+  roofline  the MaxSim kernel against the measured bf16 peak (MEASURED_PEAKS.json)
+  cpu_baseline / --impl reference: the reference's CPU path (oracle port of main.py:451-470 + :305-383) on a
+            bounded sample of the same workload, on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+NQ, ND, LQ, LD, DIM = 25000, 5000, 20, 1030, 128          # BASELINE.json configs[3]
+N_ITER, N_CI = 1000, 10000
+FLOP_PER_PAIR = 2 * LQ * LD * DIM                          # 5 273 600
+WORKLOAD = ("ColPali-v1.3 MaxSim: 25000 queries x 20 tokens vs 5000 docs x 1030 patches, 128-d bf16; "
+            "score + rank + 1000-iter bootstrap + 3 CIs")
+METRIC = "maxsim_query_doc_pairs_per_s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense 5k x 25k wall-time section")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- helpers
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return {"bf16": j["bf16_tflops"], "bf16_sustained": j.get("bf16_tflops_sustained"), "hbm": j["hbm_gbs"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_maxsim(dev, nq, nd, lq, ld, seed=2, sigma_q=1.0):
+    """docs = unit(randn(ld,128)); query tokens = unit(patch of the GT doc + sigma * unit(randn))."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(seed)
+
+    def unit(x):
+        return x / x.norm(dim=-1, keepdim=True)
+    D = unit(torch.randn(nd * ld, DIM, generator=g, device=dev)).bfloat16()
+    q2d = torch.arange(nq, device=dev) * nd // nq                     # query i -> doc i // (nq/nd)
+    rows = torch.randint(0, ld, (nq, lq), generator=g, device=dev)
+    base = D.view(nd, ld, DIM)[q2d[:, None], rows].float()
+    noise = unit(torch.randn(nq, lq, DIM, generator=g, device=dev))
+    Q = unit(base + sigma_q * noise).bfloat16().view(nq * lq, DIM)
+    return Q.contiguous(), D.contiguous(), q2d.to(torch.int32)
+
+
+def cpu_maxsim_sample(seconds: float, threads: int):
+    """The reference's CPU path for this workload: chunk loop main.py:451-470 with the fp32 `processor.score`
+    stand-in (oracle.maxsim_scores) + metrics (strict-greater restatement of main.py:331-358) on a bounded sample."""
+    import numpy as np
+    import torch
+    import oracle
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(2)
+    nd_s, nq_s = 100, 500
+
+    def unit(x):
+        return x / x.norm(dim=-1, keepdim=True)
+    docs = [unit(torch.randn(LD, DIM, generator=g)).bfloat16() for _ in range(nd_s)]
+    queries = [unit(torch.randn(LQ, DIM, generator=g)).bfloat16() for _ in range(nq_s)]
+    pairs, t0 = 0, time.perf_counter()
+    while True:
+        s = oracle.maxsim_scores(queries, docs)
+        oracle.above_gt_counts(s, [[i * nd_s // nq_s] for i in range(nq_s)])
+        pairs += nq_s * nd_s
+        dt = time.perf_counter() - t0
+        if dt > seconds:
+            break
+    return pairs / dt, f"{pairs} pairs ({nq_s} queries x {nd_s} docs blocks, 20 tok x 1030 patches x 128) in {dt:.1f} s"
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    import numpy as np
+    import torch
+    import oracle
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(2)
+
+    def unit(x):
+        return x / x.norm(dim=-1, keepdim=True)
+    nd_s, nq_s = 100, 250                                   # one step = 25 000 pairs of the cfg4 shape
+    docs = [unit(torch.randn(LD, DIM, generator=g)).bfloat16() for _ in range(nd_s)]
+    queries = [unit(torch.randn(LQ, DIM, generator=g)).bfloat16() for _ in range(nq_s)]
+    rs = np.random.RandomState(42)
+
+    def step():
+        s = oracle.maxsim_scores(queries, docs)                                   # main.py:451-470
+        thr, cnt, _ = oracle.above_gt_counts(s, [[i * nd_s // nq_s] for i in range(nq_s)])   # main.py:331-358
+        vals = 100.0 * np.array([(cnt.numpy() < k).sum() for k in (1, 5, 10)]) / nq_s
+        return vals
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = args.steps * nq_s * nd_s / dt
+    sample = f"{nq_s} queries x {nd_s} docs per step ({nq_s * nd_s} pairs of the 20 x 1030 x 128 shape), score + rank"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mmx
+    from mmx import ops, sharded
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise mmx.MmxError("bench.py needs a B200: the scoring path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 0)
+
+    # ---- synthetic inputs: every rank builds the same tensors, then keeps its contiguous shard of the documents
+    Q, D_all, q2d = synth_maxsim(dev, NQ, ND, LQ, LD)
+    bounds = sharded.shard_bounds(ND, world)
+    d0, d1 = bounds[rank]
+    D = D_all[d0 * LD:d1 * LD].clone()
+    del D_all
+    nd_loc = d1 - d0
+    q_off = torch.arange(0, NQ * LQ + 1, LQ, dtype=torch.int32, device=dev)
+    d_off = torch.arange(0, nd_loc * LD + 1, LD, dtype=torch.int32, device=dev)
+    gt_off = torch.arange(NQ + 1, dtype=torch.int32, device=dev)
+    rs = np.random.RandomState(42)
+    si_h = rs.randint(0, ND, size=(N_ITER, ND)).astype(np.int32)
+    ci_h = [rs.randint(0, N_ITER, size=(N_CI, N_ITER)).astype(np.int32) for _ in range(3)]
+    si_d = torch.from_numpy(si_h).to(dev)
+    ci_d = [torch.from_numpy(c).to(dev) for c in ci_h]
+    S = torch.empty((NQ, nd_loc), dtype=torch.float32, device=dev)
+    k2_events = []
+
+    def step(record_k2: bool):
+        if record_k2:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        ops.maxsim_scores(Q, q_off, D, d_off, None, out=S)                               # K2
+        if record_k2:
+            e1.record()
+            k2_events.append((e0, e1))
+        local = ops.rank_from_scores(S, gt_off, q2d, g_base=d0, threshold_only=True)     # KR threshold
+        thr = sharded.merge_thresholds(local.thr)
+        local = ops.rank_from_scores(S, gt_off, q2d, g_base=d0, thr=thr)                 # KR count + bitmask
+        ranks = sharded.merge_ranks(local, bounds)
+        if rank != 0:
+            return None
+        ranks.q_unit = q2d
+        mult = ops.bincount(si_d, ND)                                                    # K3
+        correct = ops.boot_counts(ranks, mult)
+        values = 100.0 * correct.to(torch.float64) / float(NQ)
+        means = [ops.ci_means(values[:, j].contiguous(), ci_d[j]) for j in range(3)]     # K4
+        return ranks, correct, means
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    last = None
+    for _ in range(K):
+        last = step(True)
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([t_start.elapsed_time(t_end) / K], device=dev)
+    k2_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in k2_events) / len(k2_events)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(k2_ms, op=dist.ReduceOp.MAX)
+    ms_per_step, k2_ms = float(ms.item()), float(k2_ms.item())
+    launches_per_step = 3 + 2 + (2 + 2 + 3 if rank == 0 else 0)   # K2(tok2q, maxsim, fixup) KR(2) bincount(2) K3(2) K4(3)
+
+    # ---- e2e: the public API from pinned host buffers (H2D + host RNG + D2H inside the timed region), wall clock
+    Qh = torch.empty(Q.shape, dtype=Q.dtype, pin_memory=True).copy_(Q)
+    Dh = torch.empty(D.shape, dtype=D.dtype, pin_memory=True).copy_(D)
+    q2d_h = q2d.cpu().numpy()
+    qv = mmx.FlatMultiVector(Qh, np.full(NQ, LQ))
+    dv = mmx.FlatMultiVector(Dh, np.full(nd_loc, LD))
+    m_info = {"type": "colpali", "name": "ColPali-synth"}
+    e2e_steps = max(1, min(K, 3))
+
+    def e2e_step(seed):
+        return mmx.run_retrieval_bootstrap(qv, dv, q2d_h, m_info, N_ITER, rng=np.random.RandomState(seed))
+    e2e_step(42)
+    barrier()
+    t0 = time.perf_counter()
+    res = None
+    for i in range(e2e_steps):
+        res = e2e_step(42)
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / e2e_steps], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    h2d = Qh.numel() * 2 + Dh.numel() * 2 + (NQ + 1 + nd_loc + 1 + NQ) * 4
+    d2h = 0
+    if rank == 0:
+        h2d += si_h.nbytes + sum(c.nbytes for c in ci_h)
+        d2h = N_ITER * 3 * 8 + 3 * N_CI * 8 + 3 * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # the device-resident step and the API step agree on the integers (same seed, same stream)
+    ranks, correct, means = last
+    vals = (100.0 * correct.to(torch.float64) / float(NQ)).cpu().numpy()
+    assert np.array_equal(vals, res["_bootstrap_values"]), "device-resident step and API step disagree"
+
+    pk = peaks()
+    total_pairs = NQ * ND
+    achieved_tf = (NQ * nd_loc * FLOP_PER_PAIR) / (k2_ms * 1e-3) / 1e12          # this rank's K2 launch
+    line = {
+        "metric": METRIC, "value": total_pairs / (ms_per_step * 1e-3), "unit": "pairs/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "n_queries": NQ, "n_docs": ND, "query_tokens": LQ, "doc_patches": LD,
+                   "dim": DIM, "bootstrap_iterations": N_ITER, "ci_resamples": N_CI,
+                   "parallelism": f"doc-shard x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs_exceed_l2 (1.32 GB of doc patches streamed per step; L2 is 126 MB)"},
+        "e2e": {"value": total_pairs / e2e_s, "unit": "pairs/s", "ms_per_step": 1e3 * e2e_s,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "note": "mmx.run_retrieval_bootstrap from pinned host buffers; includes the reference's numpy RNG "
+                        "draws on the host (overlapped with the scoring kernel); wall clock, max over ranks"},
+        "gpu_launches": launches_per_step * K,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "mmx::maxsim::maxsim_kernel", "achieved": achieved_tf,
+                     "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16"],
+                     "frac_of_sustained_peak": achieved_tf / pk["bf16_sustained"] if pk["bf16_sustained"] else None,
+                     "peak_source": pk["source"] + "; burst cuBLAS figure", "kernel_ms": k2_ms,
+                     "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": NQ * nd_loc, "traffic": None},
+        "base_recall": {f"R@{k}": v for k, v in ranks.recall().items()},
+        "ci": {k: res[k] for k in res if k.startswith("R@")},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        v, sample = cpu_maxsim_sample(args.cpu_seconds, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+    if not args.no_dense and world == 1:
+        line["dense"] = dense_section(dev, K, W)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def dense_section(dev, K, W):
+    """BASELINE.json configs[1]: SigLIP-400M shapes 5000x1152 / 25000x1152, three protocols + 1000-iteration
+    bootstrap + nine CIs (+ one permutation test), device-resident and end to end."""
+    import numpy as np
+    import torch
+    import mmx
+    from mmx import ops
+    sys.path.insert(0, str(ROOT / "tests"))
+    from helpers import synth_dense
+    N, Dm = 5000, 1152
+    img, all_txt = synth_dense(N, Dm, 10.0, seed=0)
+    t2i = all_txt[0::5].contiguous()
+    m_info = {"type": "siglip", "name": "SigLIP-synth"}
+    img_d, t2i_d, all_d = img.to(dev), t2i.to(dev), all_txt.to(dev)
+    rs = np.random.RandomState(42)
+    si_d = torch.from_numpy(rs.randint(0, N, size=(N_ITER, N)).astype(np.int32)).to(dev)
+    ci_d = [torch.from_numpy(rs.randint(0, N_ITER, size=(N_CI, N_ITER)).astype(np.int32)).to(dev) for _ in range(9)]
+
+    def step():
+        ranks = mmx.score_and_rank(img_d, t2i_d, all_d, m_info)
+        mult = ops.bincount(si_d, N)
+        cols = [ops.boot_counts(ranks[p], mult) for p in ("T2I", "I2T", "I2T_Sym")]
+        values = 100.0 * torch.cat(cols, dim=1).to(torch.float64) / float(N)
+        return [ops.ci_means(values[:, j].contiguous(), ci_d[j]) for j in range(9)]
+    for _ in range(max(W, 1)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / K
+    # end to end through the reference-signature API, host tensors in, CSV row out (host RNG included)
+    imgp, t2ip, allp = img.pin_memory(), t2i.pin_memory(), all_txt.pin_memory()
+    mmx.run_bootstrap_from_embeddings(imgp, t2ip, allp, m_info, N_ITER, rng=np.random.RandomState(42))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    row = mmx.run_bootstrap_from_embeddings(imgp, t2ip, allp, m_info, N_ITER, rng=np.random.RandomState(42))
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    p = mmx.permutation_test(row["_bootstrap_values"]["T2I_R@1"], row["_bootstrap_values"]["I2T_Sym_R@1"],
+                             rng=np.random.RandomState(7))
+    perm_ms = 1e3 * (time.perf_counter() - t0)
+    pairs = N * N * 2 + N * 5 * N
+    return {"workload": "SigLIP-400M dense scoring 5000x1152 / 25000x1152, T2I + I2T(1-to-5) + I2T_Sym, "
+                        "1000-iter bootstrap + 9 CIs (10 000 resamples each)",
+            "metric": "dense_score_rank_bootstrap_wall_ms", "device_resident_ms": dev_ms, "e2e_ms": e2e_ms,
+            "e2e_note": "mmx.run_bootstrap_from_embeddings from pinned host tensors to the 42-column row; includes "
+                        "~9.5e7 numpy random draws on the host", "permutation_test_ms": perm_ms,
+            "permutation_p": float(p), "pairs_scored": pairs,
+            "T2I_R@1": [row["T2I_R@1_mean"], row["T2I_R@1_lower"], row["T2I_R@1_upper"]],
+            "I2T_R@1": [row["I2T_R@1_mean"], row["I2T_R@1_lower"], row["I2T_R@1_upper"]]}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

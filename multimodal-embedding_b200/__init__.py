@@ -6,10 +6,10 @@ the reference's own function names and signatures (see :mod:`api`), executed by 
 ``importlib.import_module("multimodal-embedding_b200")``. No CPU fallback: without the built library and a B200 the
 compute functions raise.
 """
-from . import _lib, ops                                                     # noqa: F401
+from . import _lib, ops, sharded, failure                                   # noqa: F401
 from ._lib import MmxError, build                                           # noqa: F401
 from .api import (                                                          # noqa: F401
-    CSV_COLUMNS, METRIC_KEYS, base_metrics, bootstrap_confidence_interval, bootstrap_from_ranks, compute_metrics,
+    CSV_COLUMNS, METRIC_KEYS, FlatMultiVector, base_metrics, run_retrieval_bootstrap, bootstrap_confidence_interval, bootstrap_from_ranks, compute_metrics,
     compute_metrics_detailed, compute_similarity_scores, permutation_test, run_bootstrap_benchmark,
     run_bootstrap_from_embeddings, score_and_rank, write_results_csv,
 )

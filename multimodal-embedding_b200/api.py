@@ -331,6 +331,122 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     return aggregated
 
 
+class FlatMultiVector:
+    """Embedding hand-off format for multi-vector (ColPali) items: one flat bf16 [sum(L_i), 128] tensor
+    (CPU, pinned CPU or CUDA) plus the per-item lengths — what K2 consumes, without 30 000 small tensors."""
+
+    def __init__(self, flat: torch.Tensor, lens):
+        self.flat = flat
+        self.lens = np.asarray(lens, dtype=np.int64)
+        if int(self.lens.sum()) != flat.shape[0]:
+            raise ValueError("lens do not add up to the number of rows")
+
+    def __len__(self) -> int:
+        return len(self.lens)
+
+    @staticmethod
+    def from_list(items: Sequence[torch.Tensor]) -> "FlatMultiVector":
+        items = _as_list(items)
+        return FlatMultiVector(torch.cat(list(items), dim=0), [int(t.shape[0]) for t in items])
+
+    def slice(self, a: int, b: int) -> "FlatMultiVector":
+        off = np.concatenate([[0], np.cumsum(self.lens)])
+        return FlatMultiVector(self.flat[int(off[a]):int(off[b])], self.lens[a:b])
+
+    def to_device(self, dev: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
+        off = np.zeros(len(self.lens) + 1, dtype=np.int32)
+        off[1:] = np.cumsum(self.lens)
+        return _h2d(_as_bf16(self.flat, "multi-vector embeddings"), dev), _np_h2d(off, dev, torch.int32)
+
+
+def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: Dict, n_iterations: int, rng=None,
+                            group=None, timings: Optional[Dict[str, float]] = None) -> Optional[Dict[str, Any]]:
+    """One retrieval protocol (T2I-style: every query has one ground-truth document) scored, ranked, bootstrapped and
+    aggregated like main.py:586-651 — for the configurations whose query set is not "caption 0 of every image"
+    (BASELINE.json configs 4-5: 25 000 caption queries against 5 000 / 100 000 documents).
+
+    queries / docs: bf16 tensors [n, d] (dense) or FlatMultiVector / lists of [L_i, 128] (ColPali). The bootstrap unit
+    is the document: an iteration draws ``choice(n_docs, n_docs)`` documents, each draw brings along its queries.
+    With a torch.distributed ``group`` (world > 1) every rank passes ITS contiguous shard of the documents
+    (``sharded.shard_bounds``) and all queries; rank 0 returns the result, the others None.
+    numpy stream: n_iterations x choice(n_docs, n_docs), then 3 x 10 000 x choice(values, n_iterations)."""
+    import torch.distributed as dist
+    from . import sharded
+    dev = _device()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    q2d = np.asarray(query_to_doc, dtype=np.int32)
+    nq = len(q2d)
+    colpali = m_info["type"] == "colpali"
+    if colpali:
+        qv = queries if isinstance(queries, FlatMultiVector) else FlatMultiVector.from_list(queries)
+        dv = docs if isinstance(docs, FlatMultiVector) else FlatMultiVector.from_list(docs)
+        n_local = len(dv)
+    else:
+        n_local = docs.shape[0]
+    if world > 1:
+        sizes = torch.tensor([n_local], device=dev)
+        allsz = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(allsz, sizes, group=group)
+        ends = np.cumsum([int(s.item()) for s in allsz])
+        bounds = [(int(e - int(s.item())), int(e)) for e, s in zip(ends, allsz)]
+    else:
+        bounds = [(0, n_local)]
+    g_base, n_docs = bounds[rank][0], bounds[-1][1]
+    gt_off = torch.arange(nq + 1, dtype=torch.int32, device=dev)
+    gt_idx = _np_h2d(q2d, dev, torch.int32)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    # ---- score + threshold pass on this rank's shard (async; the host goes on to draw random numbers)
+    if colpali:
+        q_flat, q_off = qv.to_device(dev)
+        d_flat, d_off = dv.to_device(dev)
+        flags = _pad_flags(dv.lens)
+        d_zero = _np_h2d(flags, dev, torch.uint8) if flags.any() else None
+        ev[0].record()
+        S = ops.maxsim_scores(q_flat, q_off, d_flat, d_off, d_zero)
+        ev[1].record()
+        local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, threshold_only=True)
+    else:
+        Q, G = _h2d(_as_bf16(queries, "queries"), dev), _h2d(_as_bf16(docs, "docs"), dev)
+        ev[0].record()
+        local = ops.dense_rank(Q, G, gt_off, gt_idx, g_base=g_base, threshold_only=True)
+        ev[1].record()
+    # ---- the reference's numpy stream, drawn while the GPU is busy (the draws do not depend on the scores)
+    r = _rng(rng)
+    if rank == 0:
+        sample_indices = r.randint(0, n_docs, size=(n_iterations, n_docs)).astype(np.int32)     # main.py:588
+        ci_idx = [r.randint(0, n_iterations, size=(N_BOOTSTRAP, n_iterations)).astype(np.int32) for _ in KS]
+    thr = sharded.merge_thresholds(local.thr, group)
+    if colpali:
+        local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, thr=thr)
+    else:
+        local = ops.dense_rank(Q, G, gt_off, gt_idx, g_base=g_base, thr=thr)
+    ranks = sharded.merge_ranks(local, bounds, group)
+    if rank != 0:
+        return None
+    ranks.q_unit = gt_idx
+    mult = ops.bincount(_np_h2d(sample_indices, dev, torch.int32), n_docs)
+    correct = ops.boot_counts(ranks, mult)                                                       # [B, 3] int32
+    denom = mult.to(torch.float64)[:, gt_idx.long()].sum(dim=1)          # query copies drawn in each iteration
+    values = 100.0 * correct.to(torch.float64) / denom[:, None]                                  # main.py:358
+    means = [ops.ci_means(values[:, j].contiguous(), _np_h2d(ci_idx[j], dev, torch.int32)) for j in range(3)]
+    values_h = values.cpu().numpy()
+    means_h = [m.cpu().numpy() for m in means]
+    out: Dict[str, Any] = {"Model": m_info.get("name", ""), "n_queries": nq, "n_docs": n_docs}
+    alpha = (1 - 0.95) / 2
+    for j, k in enumerate(KS):
+        v = np.ascontiguousarray(values_h[:, j])
+        out[f"R@{k}_mean"] = np.mean(v)
+        out[f"R@{k}_lower"] = np.percentile(means_h[j], alpha * 100)
+        out[f"R@{k}_upper"] = np.percentile(means_h[j], (1 - alpha) * 100)
+        out[f"R@{k}_std"] = np.std(v)
+    out["base"] = ranks.recall()
+    out["_bootstrap_values"] = values_h
+    if timings is not None:
+        timings["score_ms"] = ev[0].elapsed_time(ev[1])
+    return out
+
+
 def run_bootstrap_benchmark(model, processor, m_info: Dict, dataset, n_iterations: int, *, encode_data=None,
                             load_cached_image=None, get_all_captions=None) -> Dict[str, Any]:
     """main.py:478-667. The dataset walk and the encoders stay upstream (out of scope): pass the reference's own
