@@ -105,7 +105,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def synth_maxsim(dev, nq, nd, lq, ld, seed=2, sigma_q=1.0):
+def synth_maxsim(dev, nq, nd, lq, ld, seed=2, sigma_q=3.0):
     """docs = unit(randn(ld,128)); query tokens = unit(patch of the GT doc + sigma * unit(randn))."""
     import torch
     g = torch.Generator(device=dev).manual_seed(seed)
@@ -225,6 +225,7 @@ def run_ours(args):
     si_d = torch.from_numpy(si_h).to(dev)
     ci_d = [torch.from_numpy(c).to(dev) for c in ci_h]
     S = torch.empty((NQ, nd_loc), dtype=torch.float32, device=dev)
+    nq_t = torch.tensor(float(NQ), dtype=torch.float64, device=dev)
     k2_events = []
 
     def step(record_k2: bool):
@@ -244,7 +245,7 @@ def run_ours(args):
         ranks.q_unit = q2d
         mult = ops.bincount(si_d, ND)                                                    # K3
         correct = ops.boot_counts(ranks, mult)
-        values = 100.0 * correct.to(torch.float64) / float(NQ)
+        values = 100.0 * correct.to(torch.float64) / nq_t      # tensor / tensor = IEEE division (bit-equal to numpy)
         means = [ops.ci_means(values[:, j].contiguous(), ci_d[j]) for j in range(3)]     # K4
         return ranks, correct, means
 
@@ -311,7 +312,7 @@ def run_ours(args):
 
     # the device-resident step and the API step agree on the integers (same seed, same stream)
     ranks, correct, means = last
-    vals = (100.0 * correct.to(torch.float64) / float(NQ)).cpu().numpy()
+    vals = (100.0 * correct.to(torch.float64) / nq_t).cpu().numpy()
     assert np.array_equal(vals, res["_bootstrap_values"]), "device-resident step and API step disagree"
 
     pk = peaks()
@@ -368,11 +369,13 @@ def dense_section(dev, K, W):
     si_d = torch.from_numpy(rs.randint(0, N, size=(N_ITER, N)).astype(np.int32)).to(dev)
     ci_d = [torch.from_numpy(rs.randint(0, N_ITER, size=(N_CI, N_ITER)).astype(np.int32)).to(dev) for _ in range(9)]
 
+    n_t = torch.tensor(float(N), dtype=torch.float64, device=dev)
+
     def step():
         ranks = mmx.score_and_rank(img_d, t2i_d, all_d, m_info)
         mult = ops.bincount(si_d, N)
         cols = [ops.boot_counts(ranks[p], mult) for p in ("T2I", "I2T", "I2T_Sym")]
-        values = 100.0 * torch.cat(cols, dim=1).to(torch.float64) / float(N)
+        values = 100.0 * torch.cat(cols, dim=1).to(torch.float64) / n_t
         return [ops.ci_means(values[:, j].contiguous(), ci_d[j]) for j in range(9)]
     for _ in range(max(W, 1)):
         step()
