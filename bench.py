@@ -105,7 +105,7 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def synth_maxsim(dev, nq, nd, lq, ld, seed=2, sigma_q=3.0):
+def synth_maxsim(dev, nq, nd, lq, ld, seed=2, sigma_q=5.0):
     """docs = unit(randn(ld,128)); query tokens = unit(patch of the GT doc + sigma * unit(randn))."""
     import torch
     g = torch.Generator(device=dev).manual_seed(seed)

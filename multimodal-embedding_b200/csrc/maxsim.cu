@@ -10,16 +10,20 @@
 // 1030-patch document does not have to be padded to a tile multiple.
 //
 // CTA = one persistent worker. Work item = (pair of 128-row query-token tiles A0/A1, chunk of whole documents).
-// The two A tiles stay resident in shared memory for the whole item; the chunk's patches stream through a
-// 2-stage TMA ring as 256-row B tiles. Each B tile feeds two 128x256x128 MMAs (A0*B -> TMEM cols [0,256),
-// A1*B -> TMEM cols [256,512)), so every byte of B pulled from L2 is used for 256 query rows and the two
-// accumulators ping-pong: while the tensor core fills one, an epilogue warpgroup drains the other.
+// Chunks are sized to stay resident in L2 (~24 MB of patches) while every row-tile pair sweeps over them, so HBM
+// sees each patch about once. The two A tiles stay in shared memory for the whole item; the chunk's patches
+// stream through a 2-stage TMA ring as 256-row B tiles. Each B tile feeds two 128x256x128 MMAs
+// (A0*B -> TMEM cols [0,256), A1*B -> TMEM cols [256,512)): every byte of B pulled from L2 serves 256 query rows
+// and the two accumulators ping-pong — while the tensor core fills one, the epilogue drains the other.
 //
-// Epilogue (thread == one query-token row, TMEM lane == row): running max over the row's 256 fp32 columns with
-// FMNMX3, cut at document boundaries (columns are global patch indices, boundaries come from d_off). When a
-// document ends, the 128 row maxima go through shared memory and are summed per query segment by a warp (fixed
-// shuffle tree -> deterministic), one float per (query, doc) is stored. A query whose tokens straddle two row
-// tiles gets its tail part in `carry[tile, doc]`, folded in by maxsim_fixup_kernel in tile order.
+// Epilogue: 8 warps. TMEM lane == query-token row; warps e and e+4 share a lane quarter and split the 256 columns
+// of the SAME accumulator in halves, so one accumulator is drained in half the time (the drain latency, not the
+// instruction count, is what the tensor pipe waits for). Per 32-column chunk: tcgen05.ld.32x32b.x32 + a FMNMX3 tree,
+// software-pipelined. Columns are global patch indices; document boundaries come from d_off. When a document
+// closes, both halves park their 128 row maxima in shared memory, a warp takes max(half0, half1) per row and sums
+// each query segment with a fixed shuffle tree (deterministic), and one float per (query, doc) is stored.
+// A query whose tokens straddle two row tiles gets its tail part in `carry[tile, doc]`, folded in by
+// maxsim_fixup_kernel in tile order — no floating-point atomics anywhere.
 #include <cfloat>
 #include <climits>
 
@@ -38,8 +42,11 @@ constexpr int B_HALF_BYTES = BN * 128;
 constexpr int A_TILE_BYTES = 2 * A_HALF_BYTES;   // 32 KB
 constexpr int B_STAGE_BYTES = 2 * B_HALF_BYTES;  // 64 KB
 constexpr int NSTAGE = 2;
-constexpr int NUM_THREADS = 384;                 // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, 2 x 4 epilogue
+constexpr int NUM_THREADS = 384;                 // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, 8 epilogue
+constexpr int NUM_EPI_THREADS = 256;
 constexpr int TMEM_COLS = 512;
+constexpr int HALF_COLS = BN / 2;                // columns of one accumulator drained by one warp
+constexpr long long L2_CHUNK_BYTES = 24ll << 20; // document chunk kept hot in the 126 MB L2
 
 struct Params {
     const int32_t* q_off;   // [nq+1] token offsets
@@ -56,7 +63,7 @@ struct Params {
 struct __align__(1024) Smem {
     uint8_t a[2][A_TILE_BYTES];
     uint8_t b[NSTAGE][B_STAGE_BYTES];
-    float stage[2][2][BM];  // [warpgroup][slot][row] row maxima of the document being closed
+    float stage[2][2][2][BM];  // [accumulator][slot][column half][row] row maxima of the document being closed
     int seg_start[2][BM + 1];
     int seg_q[2][BM];
     int warp_heads[2][4];
@@ -91,35 +98,35 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Per-thread state of the epilogue's walk along the patch axis.
+// Per-thread walk along the patch axis for one accumulator (= one row tile): which document the next column
+// belongs to, and the running row maximum of that document over this thread's column half.
 struct Walk {
-    int cur_doc, cur_end, d1;
+    int cur_doc, cur_end;
     float m;
     bool done;
-    int nflush;
+    int nflush, nseg, mt, cont_first;
 };
 
 struct EpiCtx {
     Smem* s;
     const Params* p;
-    int g, wq, lane, row, nseg, mt;
-    bool cont_first;
+    int e, wq, half, lane, row, d1;
 };
 
-// Close document `doc`: row maxima -> shared memory -> per-query-segment sums -> one float per (query, doc).
-// Scalars by value so the walk state stays in registers across the (rare) call.
-__device__ __noinline__ void flush_doc(Smem* sp, const Params* pp, int g, int wq, int lane, int row, int nseg,
+// Close document `doc` of accumulator g: both column halves park their row maxima, then per query segment
+// sum_r max(half0[r], half1[r]) -> one float per (query, doc). Scalars by value: the walk stays in registers.
+__device__ __noinline__ void flush_doc(Smem* sp, const Params* pp, int g, int e, int half, int lane, int row, int nseg,
                                        int mt, int cont_first, int doc, float m, int nflush) {
     const Params& p = *pp;
     Smem& s = *sp;
     if (p.d_zero != nullptr && p.d_zero[doc]) m = fmaxf(m, 0.0f);
     const int slot = nflush & 1;
-    s.stage[g][slot][row] = m;
-    named_bar_sync(1 + g, 128);
-    for (int si = (wq + nflush) & 3; si < nseg; si += 4) {
+    s.stage[g][slot][half][row] = m;
+    named_bar_sync(1, NUM_EPI_THREADS);
+    for (int si = (e + nflush) & 7; si < nseg; si += 8) {
         const int a = s.seg_start[g][si], b = s.seg_start[g][si + 1];
         float sum = 0.0f;
-        for (int r = a + lane; r < b; r += 32) sum += s.stage[g][slot][r];
+        for (int r = a + lane; r < b; r += 32) sum += fmaxf(s.stage[g][slot][0][r], s.stage[g][slot][1][r]);
         sum = warp_sum(sum);
         if (lane == 0) {
             const int q = s.seg_q[g][si];
@@ -133,23 +140,38 @@ __device__ __noinline__ void flush_doc(Smem* sp, const Params* pp, int g, int wq
     }
 }
 
-__device__ __forceinline__ void flush_doc(const EpiCtx& c, Walk& w) {
-    flush_doc(c.s, c.p, c.g, c.wq, c.lane, c.row, c.nseg, c.mt, c.cont_first ? 1 : 0, w.cur_doc, w.m, w.nflush);
+__device__ __forceinline__ void close_doc(const EpiCtx& c, Walk& w, int g) {
+    // A prefetched tcgen05.ld may still be writing its destination registers: it must land before the call below
+    // lets the compiler spill / reuse registers (no-op when nothing is in flight).
+    tmem_ld_wait();
+    flush_doc(c.s, c.p, g, c.e, c.half, c.lane, c.row, w.nseg, w.mt, w.cont_first, w.cur_doc, w.m, w.nflush);
     w.nflush++;
+    w.m = -INFINITY;
+    w.cur_doc++;
+    if (w.cur_doc >= c.d1)
+        w.done = true;
+    else
+        w.cur_end = __ldg(c.p->d_off + w.cur_doc + 1);
 }
 
-// Fold 32 accumulator columns (global patch indices [pc, pc+32)) into the walk.
-__device__ __forceinline__ void fold_chunk(const EpiCtx& c, Walk& w, const uint32_t (&v)[32], int pc) {
+__device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
+    // balanced FMNMX3 tree: 16 three-input maxima, depth 4
+    float t[11];
+#pragma unroll
+    for (int j = 0; j < 10; ++j)
+        t[j] = fmaxf(__uint_as_float(v[3 * j]), fmaxf(__uint_as_float(v[3 * j + 1]), __uint_as_float(v[3 * j + 2])));
+    t[10] = fmaxf(m, fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31])));
+    const float u0 = fmaxf(t[0], fmaxf(t[1], t[2])), u1 = fmaxf(t[3], fmaxf(t[4], t[5]));
+    const float u2 = fmaxf(t[6], fmaxf(t[7], t[8])), u3 = fmaxf(t[9], t[10]);
+    return fmaxf(fmaxf(u0, u1), fmaxf(u2, u3));
+}
+
+// Fold 32 accumulator columns this thread owns (global patch indices [pc, pc+32)) into the walk.
+__device__ __forceinline__ void fold_chunk(const EpiCtx& c, Walk& w, int g, const uint32_t (&v)[32], int pc) {
     if (w.done) return;
     int rem = w.cur_end - pc;  // columns of this chunk still owned by cur_doc
     if (rem > 32) {
-        float m0 = w.m, m1 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            m0 = fmaxf(m0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-            m1 = fmaxf(m1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-        }
-        w.m = fmaxf(m0, m1);
+        w.m = max32(v, w.m);
         return;
     }
     int lo = 0;
@@ -163,22 +185,21 @@ __device__ __forceinline__ void fold_chunk(const EpiCtx& c, Walk& w, const uint3
         }
         w.m = m;
         if (rem > 32) break;
-        flush_doc(c, w);
-        w.m = -INFINITY;
+        close_doc(c, w, g);
         lo = max(lo, hi);
-        w.cur_doc++;
-        if (w.cur_doc >= w.d1) {
-            w.done = true;
-            break;
-        }
-        w.cur_end = __ldg(c.p->d_off + w.cur_doc + 1);
+        if (w.done || lo >= 32) break;
         rem = w.cur_end - pc;
-        if (lo >= 32) break;
     }
 }
 
+// Columns [.., pend) belong to the other column half: nothing to fold, but documents that end there close here too.
+__device__ __forceinline__ void skip_to(const EpiCtx& c, Walk& w, int g, int pend) {
+    while (!w.done && w.cur_end <= pend) close_doc(c, w, g);
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d, const __grid_constant__ Params p) {
+maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
+              const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5;
@@ -197,7 +218,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.t_full[i], 1);
-            mbar_init(&s.t_empty[i], 4);  // one arrival per epilogue warp
+            mbar_init(&s.t_empty[i], 8);  // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -267,86 +288,98 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ epilogue warpgroups
+        // ------------------------------------------------------------------ epilogue (8 warps, 256 threads)
         EpiCtx c;
         c.s = &s;
         c.p = &p;
-        c.g = (warp - 4) >> 2;
-        c.wq = warp & 3;  // TMEM lane quarter this warp may read
+        c.e = warp - 4;
+        c.wq = warp & 3;        // TMEM lane quarter this warp may read
+        c.half = c.e >> 2;      // which 128 columns of every accumulator this warp drains
         c.lane = lane;
         c.row = c.wq * 32 + lane;
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(c.wq * 32) << 16) + c.g * BN;
-        uint32_t use = 0;
-        Walk w;
-        w.nflush = 0;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(c.wq * 32) << 16) + c.half * HALF_COLS;
+        uint32_t use[2] = {0, 0};
+        Walk w[2];
+        w[0].nflush = w[1].nflush = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ItemGeom g = item_geom(p, item);
-            c.mt = g.mp * 2 + c.g;
-            if (c.mt >= p.n_mtiles) continue;
-            // ---- query-segment table of this row tile
-            const int r0 = c.mt * BM;
-            const int rg = r0 + c.row;
-            const int q = rg < p.n_qtok ? __ldg(p.tok2q + rg) : -1;
-            const int qprev = (c.row == 0) ? INT_MIN : (rg - 1 < p.n_qtok ? __ldg(p.tok2q + rg - 1) : -1);
-            const bool head = q != qprev;
-            named_bar_sync(1 + c.g, 128);  // previous item's flush readers are done with the table
-            const uint32_t hmask = __ballot_sync(0xffffffffu, head);
-            if (lane == 0) s.warp_heads[c.g][c.wq] = __popc(hmask);
-            named_bar_sync(1 + c.g, 128);
-            int prefix = 0, total = 0;
+            const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
+            c.d1 = g.d1;
+            // ---- query-segment tables: the threads of column half h build the table of row tile h
+            {
+                const int tb = c.half;
+                const int mt = g.mp * 2 + tb;
+                const int r0 = mt * BM;
+                const int rg = r0 + c.row;
+                const int q = rg < p.n_qtok ? __ldg(p.tok2q + rg) : -1;
+                const int qprev = (c.row == 0) ? INT_MIN : (rg - 1 < p.n_qtok ? __ldg(p.tok2q + rg - 1) : -1);
+                const bool head = q != qprev;
+                named_bar_sync(1, NUM_EPI_THREADS);  // the previous item's readers are done with the tables
+                const uint32_t hmask = __ballot_sync(0xffffffffu, head);
+                if (lane == 0) s.warp_heads[tb][c.wq] = __popc(hmask);
+                named_bar_sync(1, NUM_EPI_THREADS);
+                int prefix = 0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int h = s.warp_heads[c.g][i];
-                if (i < c.wq) prefix += h;
-                total += h;
+                for (int i = 0; i < 4; ++i)
+                    if (i < c.wq) prefix += s.warp_heads[tb][i];
+                if (head) {
+                    const int idx = prefix + __popc(hmask & ((1u << lane) - 1u));
+                    s.seg_start[tb][idx] = c.row;
+                    s.seg_q[tb][idx] = q;
+                }
+                const int total = s.warp_heads[tb][0] + s.warp_heads[tb][1] + s.warp_heads[tb][2] + s.warp_heads[tb][3];
+                if (c.row == 0) s.seg_start[tb][total] = BM;
+                named_bar_sync(1, NUM_EPI_THREADS);
             }
-            if (head) {
-                const int idx = prefix + __popc(hmask & ((1u << lane) - 1u));
-                s.seg_start[c.g][idx] = c.row;
-                s.seg_q[c.g][idx] = q;
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int mt = g.mp * 2 + a;
+                const int r0 = mt * BM;
+                w[a].mt = mt;
+                w[a].nseg = s.warp_heads[a][0] + s.warp_heads[a][1] + s.warp_heads[a][2] + s.warp_heads[a][3];
+                w[a].cont_first = (r0 > 0) && (r0 < p.n_qtok) && (__ldg(p.tok2q + r0 - 1) == __ldg(p.tok2q + r0));
+                w[a].cur_doc = g.d0;
+                w[a].cur_end = __ldg(p.d_off + g.d0 + 1);
+                w[a].m = -INFINITY;
+                w[a].done = (g.d0 >= g.d1) || (a >= nm);
             }
-            if (c.row == 0) s.seg_start[c.g][total] = BM;
-            c.nseg = total;
-            c.cont_first = (r0 > 0) && (r0 < p.n_qtok) && (__ldg(p.tok2q + r0 - 1) == __ldg(p.tok2q + r0));
-            named_bar_sync(1 + c.g, 128);
 
-            // ---- walk the chunk's patches
-            w.cur_doc = g.d0;
-            w.d1 = g.d1;
-            w.cur_end = __ldg(p.d_off + g.d0 + 1);
-            w.m = -INFINITY;
-            w.done = g.d0 >= g.d1;
-            for (int t = 0; t < g.ntiles; ++t, ++use) {
-                mbar_wait(&s.t_full[c.g], use & 1);
-                tc_fence_after();
+            // ---- drain accumulator 0, then accumulator 1, of every B tile
+            for (int t = 0; t < g.ntiles; ++t) {
                 const int pt = g.p0 + t * BN;
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32(t_lane, va);
-                tmem_ld_wait();
-#pragma unroll 1
-                for (int ch = 0; ch < BN / 32; ch += 2) {
-                    tmem_ld_32x32(t_lane + (ch + 1) * 32, vb);
-                    fold_chunk(c, w, va, pt + ch * 32);
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    if (a >= nm) continue;
+                    mbar_wait(&s.t_full[a], use[a] & 1);
+                    use[a]++;
+                    tc_fence_after();
+                    const uint32_t ta = t_lane + a * BN;
+                    const int pc0 = pt + c.half * HALF_COLS;
+                    uint32_t va[32], vb[32];
+                    tmem_ld_32x32(ta, va);
+                    if (c.half == 1) skip_to(c, w[a], a, pc0);     // documents that end inside the other half
                     tmem_ld_wait();
-                    if (ch + 2 < BN / 32) {
-                        tmem_ld_32x32(t_lane + (ch + 2) * 32, va);
-                    } else {
-                        // every column of this accumulator is in registers: hand it back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&s.t_empty[c.g]);
-                    }
-                    fold_chunk(c, w, vb, pt + (ch + 1) * 32);
-                    if (ch + 2 < BN / 32) tmem_ld_wait();
+                    tmem_ld_32x32(ta + 32, vb);
+                    fold_chunk(c, w[a], a, va, pc0);
+                    tmem_ld_wait();
+                    tmem_ld_32x32(ta + 64, va);
+                    fold_chunk(c, w[a], a, vb, pc0 + 32);
+                    tmem_ld_wait();
+                    tmem_ld_32x32(ta + 96, vb);
+                    fold_chunk(c, w[a], a, va, pc0 + 64);
+                    tmem_ld_wait();
+                    // this warp's 128 columns are in registers: hand the accumulator back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s.t_empty[a]);
+                    fold_chunk(c, w[a], a, vb, pc0 + 96);
+                    if (c.half == 0) skip_to(c, w[a], a, pt + BN);
                 }
             }
-            // documents that end exactly at the chunk end were flushed above; what is left has no patches
-            while (!w.done) {
-                flush_doc(c, w);
-                w.m = -INFINITY;
-                w.cur_doc++;
-                if (w.cur_doc >= w.d1) w.done = true;
-            }
+            // documents that end exactly at the chunk end were closed above; what is left has no patches
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+                while (!w[a].done) close_doc(c, w[a], a);
         }
     }
 
@@ -359,12 +392,11 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 __global__ void tok2q_kernel(const int32_t* __restrict__ q_off, int nq, int n_qtok, int32_t* __restrict__ tok2q) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_qtok) return;
-    int lo = 0, hi = nq;  // find largest q with q_off[q] <= t
+    int lo = 0, hi = nq;  // largest q with q_off[q] <= t (empty queries share an offset: the last one owns the row)
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (__ldg(q_off + mid) <= t) lo = mid; else hi = mid;
     }
-    // skip empty queries that share the same offset: the owner is the LAST q with q_off[q] <= t
     tok2q[t] = lo;
 }
 
@@ -438,11 +470,18 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
     p.n_mtiles = (int)((n_qtok + BM - 1) / BM);
     p.n_mpairs = (p.n_mtiles + 1) / 2;
     const int sms = sm_count();
-    long long want_chunks = ((long long)sms * 32 + p.n_mpairs - 1) / p.n_mpairs;
-    if (want_chunks < 1) want_chunks = 1;
-    if (want_chunks > nd) want_chunks = nd;
-    p.docs_per_chunk = (int)((nd + want_chunks - 1) / want_chunks);
-    p.n_chunks = (int)((nd + p.docs_per_chunk - 1) / p.docs_per_chunk);
+    // Chunk of whole documents per work item: small enough to stay L2-resident while all row-tile pairs sweep it,
+    // and numerous enough that the persistent grid is balanced (>= 32 items per SM when the problem allows).
+    const long long avg_doc_bytes = (n_dtok * (long long)DIM * 2 + nd - 1) / nd;
+    long long dpc = L2_CHUNK_BYTES / (avg_doc_bytes > 0 ? avg_doc_bytes : 1);
+    const long long want_chunks = ((long long)sms * 32 + p.n_mpairs - 1) / p.n_mpairs;
+    const long long dpc_balance = (nd + want_chunks - 1) / want_chunks;
+    if (dpc > dpc_balance) dpc = dpc_balance;
+    if (dpc < 1) dpc = 1;
+    if (dpc > nd) dpc = nd;
+    p.docs_per_chunk = (int)dpc;
+    p.n_chunks = (int)((nd + dpc - 1) / dpc);
+    MMX_REQUIRE((long long)p.n_mpairs * p.n_chunks < (1ll << 31), "too many work items");
 
     CUtensorMap tq, td;
     if (make_tmap_bf16_sw128(&tq, q_tok, (uint64_t)n_qtok, DIM, DIM, BM) != 0) return -4;
