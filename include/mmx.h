@@ -116,6 +116,13 @@ int mmx_ci_means(const double* data, int n, const int32_t* idx, int R, double* m
 int mmx_perm_stats(const double* combined, int n1, int n2, const int32_t* perm, int P, double* diffs,
                    cudaStream_t stream);
 
+/* K6  numpy legacy MT19937 stream on the device — the draws behind np.random.choice(n, n) (main.py:588) and
+ * np.random.choice(data, n) (main.py:269), both == RandomState.randint(0, high, count):
+ * masked rejection on 32-bit MT19937 outputs. state: uint32 [625] = numpy's get_state() key[624] followed by pos;
+ * it is advanced exactly as numpy would advance it, so it can be written back with set_state().
+ * out int32 [count] = the next `count` values numpy would return for randint(0, high). 1 <= high < 2^31. */
+int mmx_mt19937_randint(uint32_t* state, uint32_t high, int64_t count, int32_t* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

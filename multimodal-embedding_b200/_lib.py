@@ -16,7 +16,7 @@ from typing import Optional
 _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 LIB_PATH = CSRC / "libmmx.so"
-SOURCES = ["mmx_host.cu", "maxsim.cu", "dense_rank.cu", "rank_scores.cu", "stats.cu"]
+SOURCES = ["mmx_host.cu", "maxsim.cu", "dense_rank.cu", "rank_scores.cu", "stats.cu", "rng.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -97,6 +97,7 @@ _SIGNATURES = {
     "mmx_ci_means": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,   # data, n, idx, R, means, stream
     ]),
+    "mmx_mt19937_randint": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p, _c.c_void_p]),
     "mmx_perm_stats": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,  # combined,n1,n2,perm,P,diffs,stream
     ]),

@@ -31,6 +31,7 @@ CSV_COLUMNS = (["Model"] + [f"{k}_{s}" for k in METRIC_KEYS for s in ("mean", "l
                + ["Time", "QPS", "Encoding_Time", "Img_per_sec", "_failure_analysis"])  # main.py:643-665
 N_BOOTSTRAP = 10000       # main.py:265
 CHUNK = 10                # main.py:453
+DEVICE_RNG = True         # draw the reference's numpy MT19937 stream on the GPU (K6); False = numpy draws on the host
 
 
 # ------------------------------------------------------------------------------------------------ plumbing
@@ -199,9 +200,16 @@ def bootstrap_confidence_interval(data: np.ndarray, confidence: float = 0.95, rn
     dev = _device()
     data = np.asarray(data)
     n = len(data)
-    idx = _rng(rng).randint(0, n, size=(N_BOOTSTRAP, n))                     # == N_BOOTSTRAP x choice
     d = _np_h2d(data.astype(np.float64, copy=False), dev, torch.float64)
-    means = ops.ci_means(d, _np_h2d(idx.astype(np.int32), dev, torch.int32)).cpu().numpy()
+    if isinstance(rng, ops.DeviceRng):
+        idx = rng.randint(n, N_BOOTSTRAP * n).view(N_BOOTSTRAP, n)           # K6: the same stream, drawn on the GPU
+    elif DEVICE_RNG:
+        drng = ops.DeviceRng(_rng(rng), dev)
+        idx = drng.randint(n, N_BOOTSTRAP * n).view(N_BOOTSTRAP, n)
+        drng.commit()                                                        # numpy's state advances as in the reference
+    else:
+        idx = _np_h2d(_rng(rng).randint(0, n, size=(N_BOOTSTRAP, n)).astype(np.int32), dev, torch.int32)
+    means = ops.ci_means(d, idx).cpu().numpy()                               # == N_BOOTSTRAP x choice + mean
     mean = np.mean(data)
     alpha = (1 - confidence) / 2
     lower = np.percentile(means, alpha * 100)
@@ -281,7 +289,10 @@ def bootstrap_from_ranks(ranks: Dict[str, ops.ProtocolRanks], sample_indices: np
     ``sample_indices`` [B, N] (main.py:588), without rescoring. With want_hits also returns, per base T2I query,
     (R@1 hits summed over iterations, times drawn) — the inputs of aggregate_failure_analysis."""
     dev = _device()
-    si = _np_h2d(np.asarray(sample_indices).astype(np.int32), dev, torch.int32)
+    if isinstance(sample_indices, torch.Tensor) and sample_indices.is_cuda:
+        si = sample_indices.to(torch.int32)
+    else:
+        si = _np_h2d(np.asarray(sample_indices).astype(np.int32), dev, torch.int32)
     mult = ops.bincount(si, n_images)
     cols = []
     hits = torch.zeros(ranks["T2I"].nq, dtype=torch.int32, device=dev) if want_hits else None
@@ -306,7 +317,11 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     t0 = time.time() if t_start is None else t_start
     n_images = len(img_embeds)
     ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info)
-    sample_indices = _rng(rng).randint(0, n_images, size=(n_iterations, n_images))        # main.py:588
+    drng = ops.DeviceRng(_rng(rng)) if DEVICE_RNG else None
+    if drng is not None:
+        sample_indices = drng.randint(n_images, n_iterations * n_images).view(n_iterations, n_images)   # main.py:588
+    else:
+        sample_indices = _rng(rng).randint(0, n_images, size=(n_iterations, n_images))
     correct, hits, drawn = bootstrap_from_ranks(ranks, sample_indices, n_images, want_hits=True)
     values = 100.0 * correct / n_images                                                    # main.py:358,368,378
     torch.cuda.synchronize()
@@ -314,7 +329,7 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     aggregated: Dict[str, Any] = {"Model": m_info["name"]}
     for j, key in enumerate(METRIC_KEYS):                                                  # main.py:644-651
         v = np.ascontiguousarray(values[:, j])
-        mean, lower, upper = bootstrap_confidence_interval(v, rng=rng)
+        mean, lower, upper = bootstrap_confidence_interval(v, rng=drng if drng is not None else rng)
         aggregated[f"{key}_mean"] = mean
         aggregated[f"{key}_lower"] = lower
         aggregated[f"{key}_upper"] = upper
@@ -324,6 +339,8 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     aggregated["QPS"] = n_images / enc
     aggregated["Encoding_Time"] = encoding_time
     aggregated["Img_per_sec"] = n_images / enc
+    if drng is not None:
+        drng.commit()
     caps = t2i_captions if t2i_captions is not None else [""] * n_images
     aggregated["_failure_analysis"] = aggregate_failure_from_hits(caps, hits, drawn)      # main.py:664
     aggregated["_bootstrap_values"] = {k: values[:, j].copy() for j, k in enumerate(METRIC_KEYS)}
@@ -357,6 +374,41 @@ class FlatMultiVector:
         off = np.zeros(len(self.lens) + 1, dtype=np.int32)
         off[1:] = np.cumsum(self.lens)
         return _h2d(_as_bf16(self.flat, "multi-vector embeddings"), dev), _np_h2d(off, dev, torch.int32)
+
+
+H2D_DOC_CHUNKS = 8   # host-resident documents are uploaded in this many pieces, each scored while the next one copies
+
+
+def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device) -> torch.Tensor:
+    """K2 over documents that still live in host memory: the upload of document chunk c+1 (copy stream, pinned
+    source) overlaps the scoring of chunk c, so PCIe time hides behind the tensor cores. Returns fp32 [nq, nd]."""
+    nq, nd = len(qv), len(dv)
+    flags = _pad_flags(dv.lens)                       # chunk-of-10 padding flags of the WHOLE list (main.py:465)
+    q_flat, q_off = qv.to_device(dev)
+    n_chunks = 1 if dv.flat.is_cuda else max(1, min(H2D_DOC_CHUNKS, nd // 64))
+    if n_chunks == 1:
+        d_flat, d_off = dv.to_device(dev)
+        return ops.maxsim_scores(q_flat, q_off, d_flat, d_off, _np_h2d(flags, dev, torch.uint8) if flags.any() else None)
+    S = torch.empty((nq, nd), dtype=torch.float32, device=dev)
+    main, copy = torch.cuda.current_stream(), torch.cuda.Stream(device=dev)
+    step = -(-nd // n_chunks)
+    staged = []
+    with torch.cuda.stream(copy):
+        for a in range(0, nd, step):
+            b = min(nd, a + step)
+            part = dv.slice(a, b)
+            d_flat, d_off = part.to_device(dev)
+            d_zero = _np_h2d(flags[a:b], dev, torch.uint8) if flags[a:b].any() else None
+            ready = torch.cuda.Event()
+            ready.record(copy)
+            staged.append((a, b, d_flat, d_off, d_zero, ready))
+    for a, b, d_flat, d_off, d_zero, ready in staged:
+        main.wait_event(ready)
+        for t in (d_flat, d_off, d_zero):
+            if t is not None:
+                t.record_stream(main)
+        ops.maxsim_scores(q_flat, q_off, d_flat, d_off, d_zero, out=S[:, a:b])
+    return S
 
 
 def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: Dict, n_iterations: int, rng=None,
@@ -393,17 +445,25 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     else:
         bounds = [(0, n_local)]
     g_base, n_docs = bounds[rank][0], bounds[-1][1]
+    # ---- the reference's numpy stream (the draws do not depend on the scores). Device mode (K6): one small CTA on a
+    # side stream regenerates MT19937 while the embeddings cross PCIe and the scoring kernel runs.
+    r = _rng(rng)
+    if rank == 0 and DEVICE_RNG:
+        side = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(side):
+            drng = ops.DeviceRng(r, dev)
+            sample_indices = drng.randint(n_docs, n_iterations * n_docs).view(n_iterations, n_docs)  # main.py:588
+            ci_idx = [drng.randint(n_iterations, N_BOOTSTRAP * n_iterations).view(N_BOOTSTRAP, n_iterations)
+                      for _ in KS]                                                                    # main.py:269
+            rng_done = torch.cuda.Event()
+            rng_done.record(side)
     gt_off = torch.arange(nq + 1, dtype=torch.int32, device=dev)
     gt_idx = _np_h2d(q2d, dev, torch.int32)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    # ---- score + threshold pass on this rank's shard (async; the host goes on to draw random numbers)
+    # ---- score + threshold pass on this rank's shard (async)
     if colpali:
-        q_flat, q_off = qv.to_device(dev)
-        d_flat, d_off = dv.to_device(dev)
-        flags = _pad_flags(dv.lens)
-        d_zero = _np_h2d(flags, dev, torch.uint8) if flags.any() else None
         ev[0].record()
-        S = ops.maxsim_scores(q_flat, q_off, d_flat, d_off, d_zero)
+        S = _maxsim_streamed(qv, dv, dev)
         ev[1].record()
         local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, threshold_only=True)
     else:
@@ -411,11 +471,12 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         ev[0].record()
         local = ops.dense_rank(Q, G, gt_off, gt_idx, g_base=g_base, threshold_only=True)
         ev[1].record()
-    # ---- the reference's numpy stream, drawn while the GPU is busy (the draws do not depend on the scores)
-    r = _rng(rng)
-    if rank == 0:
-        sample_indices = r.randint(0, n_docs, size=(n_iterations, n_docs)).astype(np.int32)     # main.py:588
-        ci_idx = [r.randint(0, n_iterations, size=(N_BOOTSTRAP, n_iterations)).astype(np.int32) for _ in KS]
+    if rank == 0 and not DEVICE_RNG:
+        # host mode: numpy draws while the GPU is busy with the kernels queued above
+        sample_indices = _np_h2d(r.randint(0, n_docs, size=(n_iterations, n_docs)).astype(np.int32), dev,
+                                 torch.int32)                                                   # main.py:588
+        ci_idx = [_np_h2d(r.randint(0, n_iterations, size=(N_BOOTSTRAP, n_iterations)).astype(np.int32), dev,
+                          torch.int32) for _ in KS]
     thr = sharded.merge_thresholds(local.thr, group)
     if colpali:
         local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, thr=thr)
@@ -425,11 +486,15 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     if rank != 0:
         return None
     ranks.q_unit = gt_idx
-    mult = ops.bincount(_np_h2d(sample_indices, dev, torch.int32), n_docs)
+    if DEVICE_RNG:
+        torch.cuda.current_stream().wait_event(rng_done)
+    mult = ops.bincount(sample_indices, n_docs)
     correct = ops.boot_counts(ranks, mult)                                                       # [B, 3] int32
     denom = mult.to(torch.float64)[:, gt_idx.long()].sum(dim=1)          # query copies drawn in each iteration
     values = 100.0 * correct.to(torch.float64) / denom[:, None]                                  # main.py:358
-    means = [ops.ci_means(values[:, j].contiguous(), _np_h2d(ci_idx[j], dev, torch.int32)) for j in range(3)]
+    means = [ops.ci_means(values[:, j].contiguous(), ci_idx[j]) for j in range(3)]
+    if DEVICE_RNG:
+        drng.commit()                                                    # numpy's generator ends where the reference's would
     values_h = values.cpu().numpy()
     means_h = [m.cpu().numpy() for m in means]
     out: Dict[str, Any] = {"Model": m_info.get("name", ""), "n_queries": nq, "n_docs": n_docs}

@@ -445,7 +445,8 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
     if (nq == 0 || nd == 0) return 0;
     if (mmx_device_check() != 0) return -3;
     // every (q, d) with at least one token is overwritten; empty queries score 0
-    MMX_CHECK_CUDA(cudaMemsetAsync(scores, 0, (size_t)nq * ld_scores * sizeof(float), stream));
+    MMX_CHECK_CUDA(cudaMemset2DAsync(scores, (size_t)ld_scores * sizeof(float), 0, (size_t)nd * sizeof(float),
+                                     (size_t)nq, stream));
     if (n_qtok == 0) return 0;
     size_t need = 0;
     mmx_maxsim_workspace_bytes(n_qtok, nd, &need);

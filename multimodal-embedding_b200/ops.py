@@ -223,3 +223,32 @@ def perm_stats(combined: torch.Tensor, n1: int, perm: torch.Tensor) -> torch.Ten
     out = torch.empty((P,), dtype=torch.float64, device=combined.device)
     _lib.check(_lib.lib().mmx_perm_stats(combined.data_ptr(), n1, n - n1, perm.data_ptr(), P, out.data_ptr(), _stream()))
     return out
+
+
+class DeviceRng:
+    """numpy's legacy MT19937 stream continued on the device (K6).
+
+    ``DeviceRng(np.random)`` / ``DeviceRng(RandomState(42))`` snapshots the generator state onto the GPU; ``randint``
+    then yields exactly the values the numpy object would have produced next (the ``choice(n, n)`` /
+    ``choice(data, n)`` draws of main.py:588,269) as a CUDA int32 tensor; ``commit()`` writes the advanced state back
+    into the numpy object, so the host stream continues as if numpy itself had made the draws."""
+
+    def __init__(self, source, device: Optional[torch.device] = None):
+        self.source = np.random if source is None else source
+        st = self.source.get_state()
+        if st[0] != "MT19937":
+            raise ValueError("DeviceRng needs numpy's legacy MT19937 RandomState")
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        host = np.concatenate([np.asarray(st[1], dtype=np.uint32), np.array([st[2]], dtype=np.uint32)])
+        self.state = torch.from_numpy(host.view(np.int32).copy()).to(dev)
+
+    def randint(self, high: int, count: int) -> torch.Tensor:
+        out = torch.empty((count,), dtype=torch.int32, device=self.state.device)
+        _lib.check(_lib.lib().mmx_mt19937_randint(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
+                                                  _stream()))
+        return out
+
+    def commit(self) -> None:
+        host = self.state.cpu().numpy().view(np.uint32)
+        st = self.source.get_state()
+        self.source.set_state(("MT19937", host[:624].copy(), int(host[624]), st[3], st[4]))

@@ -323,6 +323,45 @@ def test_ci_means_bit_exact_any_length(mmx_mod, n):
             assert np.array_equal(d, w)
 
 
+# ----------------------------------------------------------------------------------------------- numpy stream on the device (K6)
+@pytest.mark.parametrize("high", [2, 3, 1000, 5000, 25000, 100000, 1 << 20, (1 << 31) - 1])
+def test_device_rng_matches_numpy_stream(mmx_mod, high):
+    """K6 continues numpy's legacy MT19937 stream bit for bit: same values as RandomState.randint(0, high, n)
+    (== the choice() calls of main.py:588,269), same generator state afterwards, interleavable with host draws."""
+    rs_dev, rs_ref = np.random.RandomState(1234), np.random.RandomState(1234)
+    for r in (rs_dev, rs_ref):
+        r.randint(0, 77, size=1001)                       # start in the middle of a 624-word block
+        r.standard_normal(3)                              # leaves a cached gaussian in the state
+    for count in (1, 623, 624, 5000, 200003):
+        d = mmx_mod.ops.DeviceRng(rs_dev)
+        got = d.randint(high, count).cpu().numpy()
+        d.commit()
+        want = rs_ref.randint(0, high, size=count)
+        assert np.array_equal(got.astype(np.int64), want)
+        a, b = rs_dev.get_state(), rs_ref.get_state()
+        assert np.array_equal(a[1], b[1]) and a[2:] == b[2:]
+        assert rs_dev.randint(0, 1 << 30) == rs_ref.randint(0, 1 << 30)       # host draws continue identically
+    d = mmx_mod.ops.DeviceRng(rs_dev)
+    assert int(d.randint(1, 10).abs().sum()) == 0                              # numpy draws nothing for high == 1
+    d.commit()
+    assert rs_dev.randint(0, 1 << 30) == rs_ref.randint(0, 1 << 30)
+
+
+def test_device_rng_global_stream_and_host_mode_agree(mmx_mod, golden_dir, monkeypatch):
+    """bootstrap_confidence_interval on the GLOBAL np.random stream: device-drawn (default) and host-drawn index
+    streams give the same tuple and leave np.random in the same state as the reference's 10 000 choice() calls."""
+    z = np.load(golden_dir / "stats.npz")
+    np.random.seed(int(z["ci_seed"]))
+    got_dev = mmx_mod.bootstrap_confidence_interval(z["ci_data"])
+    after_dev = np.random.randint(0, 1 << 30)
+    monkeypatch.setattr(mmx_mod.api, "DEVICE_RNG", False)
+    np.random.seed(int(z["ci_seed"]))
+    got_host = mmx_mod.bootstrap_confidence_interval(z["ci_data"])
+    after_host = np.random.randint(0, 1 << 30)
+    assert got_dev == got_host == (float(z["ci_mean"]), float(z["ci_lower"]), float(z["ci_upper"]))
+    assert after_dev == after_host
+
+
 # ----------------------------------------------------------------------------------------------- end to end
 def test_run_bootstrap_from_embeddings_vs_oracle(mmx_mod):
     """The whole post-encoder pipeline on a dense model: CSV row == oracle row built from the literal reference loop
