@@ -16,29 +16,25 @@
 // (A0*B -> TMEM cols [0,256), A1*B -> TMEM cols [256,512)): every byte of B pulled from L2 serves 256 query rows
 // and the two accumulators ping-pong — while the tensor core fills one, the epilogue drains the other.
 //
-// Warp roles (12 warps):
-//   0      TMA producer (one elected thread)
-//   1      MMA issuer (one elected thread, tcgen05.mma.cta_group::1.kind::f16)
-//   2      TMEM allocator
-//   3      reducer: turns the row maxima of a finished document into per-query sums and stores them
-//   4..11  drain warps. TMEM lane == query-token row; warps e and e+4 share a lane quarter and split the 256
-//          columns of the SAME accumulator in halves, so an accumulator is back with the tensor core after ~300 clk.
-//          Per 32-column chunk: tcgen05.ld.32x32b.x32 + an FMNMX3 tree, software-pipelined.
-// Columns are global patch indices; document boundaries come from d_off. When a document closes, the drain warps
-// only park their 128 row maxima (per column half) in a shared-memory slot and arrive on an mbarrier; the reducer
-// warp takes max(half0, half1) per row, sums each query segment with a fixed shuffle tree (deterministic) and stores
-// one float per (query, doc) — the drain warps never wait for that work. A query whose tokens straddle two row
-// tiles gets its tail part in `carry[tile, doc]`, folded in by maxsim_fixup_kernel in tile order — no floating-point
-// atomics anywhere.
+// Epilogue: 8 warps. TMEM lane == query-token row; warps e and e+4 share a lane quarter and split the 256 columns
+// of the SAME accumulator in halves, so one accumulator is drained in half the time (the drain latency, not the
+// instruction count, is what the tensor pipe waits for). Per 32-column chunk: tcgen05.ld.32x32b.x32 + a FMNMX3 tree,
+// software-pipelined. Columns are global patch indices; document boundaries come from d_off. When a document
+// closes, both halves park their 128 row maxima in shared memory, a warp takes max(half0, half1) per row and sums
+// each query segment with a fixed shuffle tree (deterministic), and one float per (query, doc) is stored.
+// A query whose tokens straddle two row tiles gets its tail part in `carry[tile, doc]`, folded in by
+// maxsim_fixup_kernel in tile order — no floating-point atomics anywhere.
 #include <cfloat>
 #include <climits>
 
-#include "../../include/mmx.h"
-#include "mmx_host.cuh"
-#include "sm100_ptx.cuh"
+#include "../include/mmx.h"
+#include "../multimodal-embedding_b200/csrc/mmx_host.cuh"
+#include "../multimodal-embedding_b200/csrc/sm100_ptx.cuh"
 
 namespace mmx {
 namespace maxsim {
+__device__ unsigned long long g_prof[148*16*8];
+#define PROF(slot, expr) do { long long _t0 = clock64(); expr; prof[slot] += clock64() - _t0; } while (0)
 
 constexpr int BM = 128;                          // query-token rows per MMA (TMEM lanes)
 constexpr int BN = 256;                          // document patches per MMA (TMEM columns)
@@ -48,10 +44,10 @@ constexpr int B_HALF_BYTES = BN * 128;
 constexpr int A_TILE_BYTES = 2 * A_HALF_BYTES;   // 32 KB
 constexpr int B_STAGE_BYTES = 2 * B_HALF_BYTES;  // 64 KB
 constexpr int NSTAGE = 2;
-constexpr int NUM_THREADS = 384;
+constexpr int NUM_THREADS = 384;                 // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, 8 epilogue
+constexpr int NUM_EPI_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 constexpr int HALF_COLS = BN / 2;                // columns of one accumulator drained by one warp
-constexpr int NSLOT = 4;                         // parked-document slots per accumulator
 constexpr long long L2_CHUNK_BYTES = 24ll << 20; // document chunk kept hot in the 126 MB L2
 
 struct Params {
@@ -69,13 +65,13 @@ struct Params {
 struct __align__(1024) Smem {
     uint8_t a[2][A_TILE_BYTES];
     uint8_t b[NSTAGE][B_STAGE_BYTES];
-    float stage[2][NSLOT][2][BM];  // [accumulator][slot][column half][row] row maxima of a closed document
-    int seg_start[2][BM + 1];      // reducer-private: query segments of the two row tiles
+    float stage[2][2][2][BM];  // [accumulator][slot][column half][row] row maxima of the document being closed
+    int seg_start[2][BM + 1];
     int seg_q[2][BM];
+    int warp_heads[2][4];
     uint64_t a_full, a_free;
     uint64_t b_full[NSTAGE], b_empty[NSTAGE];
     uint64_t t_full[2], t_empty[2];
-    uint64_t st_full[2][NSLOT], st_empty[2][NSLOT];
     uint32_t tmem_base;
 };
 
@@ -104,50 +100,71 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// ---------------------------------------------------------------------------------------------- drain warps
 // Per-thread walk along the patch axis for one accumulator (= one row tile): which document the next column
 // belongs to, and the running row maximum of that document over this thread's column half.
 struct Walk {
-    int cur_doc, cur_end, next_end;  // next_end = end of cur_doc+1, prefetched so a boundary never waits on HBM
+    int cur_doc, cur_end;
     float m;
     int done;
-    uint32_t nposted;  // documents parked so far (slot = nposted % NSLOT)
-    uint32_t use;      // how many times this accumulator has been drained (mbarrier phase)
+    int nflush, nseg, mt, cont_first;
+    uint32_t use;  // how many times this accumulator has been drained (mbarrier phase)
 };
 
 struct EpiCtx {
     Smem* s;
     const Params* p;
-    int half, lane, row, d1;
+    int e, wq, half, lane, row, d1;
 };
 
-// cur_doc is complete for this thread's columns: park the row maximum for the reducer and move to the next doc.
+// Close document `doc` of accumulator g: both column halves park their row maxima, then per query segment
+// sum_r max(half0[r], half1[r]) -> one float per (query, doc). Scalars by value: the walk stays in registers.
+__device__ __noinline__ void flush_doc(Smem* sp, const Params* pp, int g, int e, int half, int lane, int row, int nseg,
+                                       int mt, int cont_first, int doc, float m, int nflush) {
+    const Params& p = *pp;
+    Smem& s = *sp;
+    if (p.d_zero != nullptr && p.d_zero[doc]) m = fmaxf(m, 0.0f);
+    const int slot = nflush & 1;
+    s.stage[g][slot][half][row] = m;
+    named_bar_sync(1, NUM_EPI_THREADS);
+    for (int si = (e + nflush) & 7; si < nseg; si += 8) {
+        const int a = s.seg_start[g][si], b = s.seg_start[g][si + 1];
+        float sum = 0.0f;
+        for (int r = a + lane; r < b; r += 32) sum += fmaxf(s.stage[g][slot][0][r], s.stage[g][slot][1][r]);
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            const int q = s.seg_q[g][si];
+            if (q >= 0) {
+                if (si == 0 && cont_first)
+                    p.carry[(long long)mt * p.nd + doc] = sum;
+                else
+                    p.scores[(long long)q * p.ld_scores + doc] = sum;
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void close_doc(const EpiCtx& c, Walk& w, int g) {
-    Smem& s = *c.s;
-    const uint32_t slot = w.nposted % NSLOT, round = w.nposted / NSLOT;
-    mbar_wait(&s.st_empty[g][slot], (round & 1) ^ 1);  // the reducer has consumed this slot's previous document
-    s.stage[g][slot][c.half][c.row] = w.m;
-    __syncwarp();
-    if (c.lane == 0) mbar_arrive(&s.st_full[g][slot]);
-    w.nposted++;
+    // A prefetched tcgen05.ld may still be writing its destination registers: it must land before the call below
+    // lets the compiler spill / reuse registers (no-op when nothing is in flight).
+    tmem_ld_wait();
+    flush_doc(c.s, c.p, g, c.e, c.half, c.lane, c.row, w.nseg, w.mt, w.cont_first, w.cur_doc, w.m, w.nflush);
+    w.nflush++;
     w.m = -INFINITY;
     w.cur_doc++;
-    w.cur_end = w.next_end;
-    if (w.cur_doc >= c.d1) {
+    if (w.cur_doc >= c.d1)
         w.done = 1;
-    } else if (w.cur_doc + 1 < c.d1) {
-        w.next_end = __ldg(c.p->d_off + w.cur_doc + 2);
-    }
+    else
+        w.cur_end = __ldg(c.p->d_off + w.cur_doc + 1);
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c) {
     float r;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));   // FMNMX3
     return r;
 }
 
-// max(m, v[0..32)): four independent FMNMX3 chains of depth 4 plus two combines (asm-pinned so that ptxas does not
-// re-serialise the associative maxima into two long dependent chains).
+// max(m, v[0..32)): four independent FMNMX3 chains of depth 4, then two combines (asm-pinned so that ptxas does
+// not re-serialise the associative maxima into two long dependent chains).
 __device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
     float c0 = max3(m, __uint_as_float(v[0]), __uint_as_float(v[1]));
     float c1 = max3(__uint_as_float(v[2]), __uint_as_float(v[3]), __uint_as_float(v[4]));
@@ -163,11 +180,11 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32], float m) {
     c0 = max3(c0, __uint_as_float(v[27]), __uint_as_float(v[28]));
     c1 = max3(c1, __uint_as_float(v[29]), __uint_as_float(v[30]));
     c2 = fmaxf(c2, __uint_as_float(v[31]));
-    return fmaxf(max3(c0, c1, c2), c3);
+    return max3(max3(c0, c1, c2), c3, c3);
 }
 
 // Fold 32 accumulator columns this thread owns (global patch indices [pc, pc+32)) into the walk; documents may end
-// anywhere inside the chunk.
+// anywhere inside the chunk (general path, kept small: it runs once per document per row tile, not per tile).
 __device__ __forceinline__ void fold_chunk_general(const EpiCtx& c, Walk& w, int g, const uint32_t (&v)[32], int pc) {
     if (w.done) return;
     int rem = w.cur_end - pc;  // columns of this chunk still owned by cur_doc
@@ -206,17 +223,19 @@ __device__ __forceinline__ void release_accumulator(Smem& s, int a, int lane) {
 }
 
 // Drain this warp's 128 columns of accumulator `a` for the B tile that starts at patch `pt`.
-__device__ __forceinline__ void drain_accumulator(const EpiCtx& c, Smem& s, Walk& w, int a, uint32_t t_lane, int pt) {
-    mbar_wait(&s.t_full[a], w.use & 1);
+__device__ __forceinline__ void drain_accumulator(const EpiCtx& c, Smem& s, Walk& w, int a, uint32_t t_lane, int pt, long long* prof) {
+    { long long _t0 = clock64(); mbar_wait(&s.t_full[a], w.use & 1); prof[0] += clock64() - _t0; }
     w.use++;
+    long long _td = clock64();
     tc_fence_after();
     const uint32_t ta = t_lane + a * BN;
     const int pc0 = pt + c.half * HALF_COLS;
-    uint32_t va[32], vb[32];
-    tmem_ld_32x32(ta, va);
+    uint32_t va[32];
     if (!w.done && w.cur_end - pt > BN) {
+        uint32_t vb[32];
         // interior tile (3 of 4 at 1030 patches per document): every column belongs to cur_doc — straight-line,
         // the next chunk's TMEM load is in flight while the current one goes through the FMNMX3 tree.
+        tmem_ld_32x32(ta, va);
         tmem_ld_wait();
         tmem_ld_32x32(ta + 32, vb);
         float m = max32(va, w.m);
@@ -228,91 +247,21 @@ __device__ __forceinline__ void drain_accumulator(const EpiCtx& c, Smem& s, Walk
         m = max32(va, m);
         tmem_ld_wait();
         release_accumulator(s, a, c.lane);
+        prof[1] += clock64() - _td; prof[4]++;
         w.m = max32(vb, m);
+        prof[2] += clock64() - _td;
     } else {
-        // a document (or the chunk of documents) ends inside this tile; closing a document costs a shared-memory
-        // store and an mbarrier arrive, so the same pipeline shape still works
-        tmem_ld_wait();
-        tmem_ld_32x32(ta + 32, vb);
+        // a document ends (or the chunk of documents ends) inside this tile: one compact loop, one chunk at a time
         if (c.half == 1) skip_to(c, w, a, pc0);  // documents that end inside the other half's columns
-        fold_chunk_general(c, w, a, va, pc0);
-        tmem_ld_wait();
-        tmem_ld_32x32(ta + 64, va);
-        fold_chunk_general(c, w, a, vb, pc0 + 32);
-        tmem_ld_wait();
-        tmem_ld_32x32(ta + 96, vb);
-        fold_chunk_general(c, w, a, va, pc0 + 64);
-        tmem_ld_wait();
-        release_accumulator(s, a, c.lane);
-        fold_chunk_general(c, w, a, vb, pc0 + 96);
+#pragma unroll 1
+        for (int ch = 0; ch < HALF_COLS / 32; ++ch) {
+            tmem_ld_32x32(ta + ch * 32, va);
+            tmem_ld_wait();
+            if (ch == HALF_COLS / 32 - 1) release_accumulator(s, a, c.lane);
+            fold_chunk_general(c, w, a, va, pc0 + ch * 32);
+        }
+        prof[3] += clock64() - _td; prof[5]++;
         if (c.half == 0) skip_to(c, w, a, pt + BN);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- reducer warp
-// Query-segment table of one 128-row tile: seg_start[0..nseg] row boundaries, seg_q[s] query id (-1 = padding rows).
-__device__ __forceinline__ int build_segments(Smem& s, const Params& p, int tb, int mt, int lane) {
-    const int r0 = mt * BM;
-    int nseg = 0;
-#pragma unroll 1
-    for (int k = 0; k < BM / 32; ++k) {
-        const int row = k * 32 + lane;
-        const int rg = r0 + row;
-        const int q = rg < p.n_qtok ? __ldg(p.tok2q + rg) : -1;
-        const int qprev = (row == 0) ? INT_MIN : (rg - 1 < p.n_qtok ? __ldg(p.tok2q + rg - 1) : -1);
-        const bool head = q != qprev;
-        const uint32_t hmask = __ballot_sync(0xffffffffu, head);
-        if (head) {
-            const int idx = nseg + __popc(hmask & ((1u << lane) - 1u));
-            s.seg_start[tb][idx] = row;
-            s.seg_q[tb][idx] = q;
-        }
-        nseg += __popc(hmask);
-    }
-    if (lane == 0) s.seg_start[tb][nseg] = BM;
-    __syncwarp();
-    return nseg;
-}
-
-struct Reducer {
-    int nseg, mt, cont_first;
-    uint32_t nposted;
-};
-
-// One closed document of accumulator g: wait for the 8 drain warps, sum_r max(half0[r], half1[r]) per query segment.
-__device__ __forceinline__ void reduce_doc(Smem& s, const Params& p, Reducer& r, int g, int doc, int lane) {
-    const uint32_t slot = r.nposted % NSLOT, round = r.nposted / NSLOT;
-    mbar_wait(&s.st_full[g][slot], round & 1);
-    const bool zero = p.d_zero != nullptr && p.d_zero[doc] != 0;
-    float v[BM / 32];
-#pragma unroll
-    for (int k = 0; k < BM / 32; ++k) {
-        const int row = k * 32 + lane;
-        float x = fmaxf(s.stage[g][slot][0][row], s.stage[g][slot][1][row]);
-        v[k] = zero ? fmaxf(x, 0.0f) : x;
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s.st_empty[g][slot]);  // values are in registers: the slot can be reused
-    r.nposted++;
-#pragma unroll 1
-    for (int si = 0; si < r.nseg; ++si) {
-        const int a = s.seg_start[g][si], b = s.seg_start[g][si + 1];
-        float sum = 0.0f;
-#pragma unroll
-        for (int k = 0; k < BM / 32; ++k) {
-            const int row = k * 32 + lane;
-            sum += (row >= a && row < b) ? v[k] : 0.0f;
-        }
-        sum = warp_sum(sum);
-        if (lane == 0) {
-            const int q = s.seg_q[g][si];
-            if (q >= 0) {
-                if (si == 0 && r.cont_first)
-                    p.carry[(long long)r.mt * p.nd + doc] = sum;
-                else
-                    p.scores[(long long)q * p.ld_scores + doc] = sum;
-            }
-        }
     }
 }
 
@@ -337,11 +286,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.t_full[i], 1);
-            mbar_init(&s.t_empty[i], 8);  // one arrival per drain warp
-            for (int j = 0; j < NSLOT; ++j) {
-                mbar_init(&s.st_full[i][j], 8);
-                mbar_init(&s.st_empty[i][j], 1);
-            }
+            mbar_init(&s.t_empty[i], 8);  // one arrival per epilogue warp
         }
         fence_mbar_init();
     }
@@ -382,7 +327,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         // ------------------------------------------------------------------ MMA issuer (one thread)
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-            uint32_t it = 0, bcount = 0, use[2] = {0, 0};
+            uint32_t it = 0, bcount = 0, use[2] = {0, 0}; long long prof[8] = {0,0,0,0,0,0,0,0}; long long _tstart = clock64();
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const ItemGeom g = item_geom(p, item);
                 const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
@@ -390,10 +335,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 tc_fence_after();
                 for (int t = 0; t < g.ntiles; ++t, ++bcount) {
                     const uint32_t st = bcount % NSTAGE, ph = (bcount / NSTAGE) & 1;
-                    mbar_wait(&s.b_full[st], ph);
+                    PROF(0, mbar_wait(&s.b_full[st], ph));
                     tc_fence_after();
                     for (int m = 0; m < nm; ++m) {
-                        mbar_wait(&s.t_empty[m], (use[m] & 1) ^ 1);
+                        PROF(1 + m, mbar_wait(&s.t_empty[m], (use[m] & 1) ^ 1));
                         tc_fence_after();
 #pragma unroll
                         for (int k = 0; k < DIM / 16; ++k) {
@@ -409,75 +354,88 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 }
                 umma_commit(&s.a_free);
             }
-        }
-    } else if (warp == 3) {
-        // ------------------------------------------------------------------ reducer: replays the drain warps'
-        // sequence of closed documents (it depends on d_off only) and finishes each one
-        Reducer r[2];
-        r[0].nposted = r[1].nposted = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const ItemGeom g = item_geom(p, item);
-            const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
-            int cur[2];
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const int mt = g.mp * 2 + a;
-                const int r0 = mt * BM;
-                r[a].mt = mt;
-                r[a].cont_first = (r0 > 0) && (r0 < p.n_qtok) && (__ldg(p.tok2q + r0 - 1) == __ldg(p.tok2q + r0));
-                r[a].nseg = (a < nm) ? build_segments(s, p, a, mt, lane) : 0;
-                cur[a] = (a < nm) ? g.d0 : g.d1;
-            }
-            for (int t = 0; t < g.ntiles; ++t) {
-                const int pend = g.p0 + (t + 1) * BN;
-#pragma unroll
-                for (int a = 0; a < 2; ++a)
-                    while (cur[a] < g.d1 && __ldg(p.d_off + cur[a] + 1) <= pend) {
-                        reduce_doc(s, p, r[a], a, cur[a], lane);
-                        cur[a]++;
-                    }
-            }
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-                while (cur[a] < g.d1) {  // trailing documents without patches
-                    reduce_doc(s, p, r[a], a, cur[a], lane);
-                    cur[a]++;
-                }
+            prof[6] = clock64() - _tstart;
+            for (int i = 0; i < 8; ++i) g_prof[(blockIdx.x * 16 + 1) * 8 + i] = prof[i];
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------------ drain warps (8 warps, 256 threads)
+        // ------------------------------------------------------------------ epilogue (8 warps, 256 threads)
         EpiCtx c;
         c.s = &s;
         c.p = &p;
-        c.half = (warp - 4) >> 2;  // which 128 columns of every accumulator this warp drains
+        c.e = warp - 4;
+        c.wq = warp & 3;        // TMEM lane quarter this warp may read
+        c.half = c.e >> 2;      // which 128 columns of every accumulator this warp drains
         c.lane = lane;
-        c.row = (warp & 3) * 32 + lane;  // TMEM lane quarter = warp % 4
-        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + c.half * HALF_COLS;
+        c.row = c.wq * 32 + lane;
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(c.wq * 32) << 16) + c.half * HALF_COLS;
+        long long prof[8] = {0,0,0,0,0,0,0,0}; long long _tstart = clock64();
         Walk w0, w1;
-        w0.nposted = w1.nposted = 0;
+        w0.nflush = w1.nflush = 0;
         w0.use = w1.use = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ItemGeom g = item_geom(p, item);
             const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
             c.d1 = g.d1;
-            const int e0 = __ldg(p.d_off + g.d0 + 1);
-            const int e1 = (g.d0 + 1 < g.d1) ? __ldg(p.d_off + g.d0 + 2) : e0;
-            w0.cur_doc = w1.cur_doc = g.d0;
-            w0.cur_end = w1.cur_end = e0;
-            w0.next_end = w1.next_end = e1;
-            w0.m = w1.m = -INFINITY;
-            w0.done = (g.d0 >= g.d1);
-            w1.done = (g.d0 >= g.d1) || (nm < 2);
+            // ---- query-segment tables: the threads of column half h build the table of row tile h
+            {
+                const int tb = c.half;
+                const int mt = g.mp * 2 + tb;
+                const int r0 = mt * BM;
+                const int rg = r0 + c.row;
+                const int q = rg < p.n_qtok ? __ldg(p.tok2q + rg) : -1;
+                const int qprev = (c.row == 0) ? INT_MIN : (rg - 1 < p.n_qtok ? __ldg(p.tok2q + rg - 1) : -1);
+                const bool head = q != qprev;
+                named_bar_sync(1, NUM_EPI_THREADS);  // the previous item's readers are done with the tables
+                const uint32_t hmask = __ballot_sync(0xffffffffu, head);
+                if (lane == 0) s.warp_heads[tb][c.wq] = __popc(hmask);
+                named_bar_sync(1, NUM_EPI_THREADS);
+                int prefix = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < c.wq) prefix += s.warp_heads[tb][i];
+                if (head) {
+                    const int idx = prefix + __popc(hmask & ((1u << lane) - 1u));
+                    s.seg_start[tb][idx] = c.row;
+                    s.seg_q[tb][idx] = q;
+                }
+                const int total = s.warp_heads[tb][0] + s.warp_heads[tb][1] + s.warp_heads[tb][2] + s.warp_heads[tb][3];
+                if (c.row == 0) s.seg_start[tb][total] = BM;
+                named_bar_sync(1, NUM_EPI_THREADS);
+            }
+            auto init_walk = [&](Walk& w, int a) {
+                const int mt = g.mp * 2 + a;
+                const int r0 = mt * BM;
+                w.mt = mt;
+                w.nseg = s.warp_heads[a][0] + s.warp_heads[a][1] + s.warp_heads[a][2] + s.warp_heads[a][3];
+                w.cont_first = (r0 > 0) && (r0 < p.n_qtok) && (__ldg(p.tok2q + r0 - 1) == __ldg(p.tok2q + r0));
+                w.cur_doc = g.d0;
+                w.cur_end = __ldg(p.d_off + g.d0 + 1);
+                w.m = -INFINITY;
+                w.done = (g.d0 >= g.d1) || (a >= nm);
+            };
+            init_walk(w0, 0);
+            init_walk(w1, 1);
+
+            // ---- drain accumulator 0, then accumulator 1, of every B tile
 #pragma unroll 1
             for (int t = 0; t < g.ntiles; ++t) {
                 const int pt = g.p0 + t * BN;
-                drain_accumulator(c, s, w0, 0, t_lane, pt);
-                if (nm == 2) drain_accumulator(c, s, w1, 1, t_lane, pt);
+#pragma unroll 1
+                for (int a = 0; a < nm; ++a) {
+                    drain_accumulator(c, s, w0, a, t_lane, pt, prof);   // one instance of the drain code for both
+                    if (nm == 2) {                                  // accumulators: swap the two walks instead
+                        const Walk tmp = w0;
+                        w0 = w1;
+                        w1 = tmp;
+                    }
+                }
             }
             // documents that end exactly at the chunk end were closed above; what is left has no patches
             while (!w0.done) close_doc(c, w0, 0);
             while (!w1.done) close_doc(c, w1, 1);
         }
+        prof[6] = clock64() - _tstart;
+        if (lane == 0) for (int i = 0; i < 8; ++i) g_prof[(blockIdx.x * 16 + warp) * 8 + i] = prof[i];
     }
 
     tc_fence_before();
@@ -520,6 +478,7 @@ __global__ void maxsim_fixup_kernel(const int32_t* __restrict__ tok2q, const int
 using namespace mmx;
 using namespace mmx::maxsim;
 
+extern "C" int mmxp_get_prof(unsigned long long* host) { return (int)cudaMemcpyFromSymbol(host, mmx::maxsim::g_prof, sizeof(unsigned long long)*148*16*8); }
 extern "C" int mmx_maxsim_workspace_bytes(int64_t n_qtok, int64_t nd, size_t* bytes) {
     MMX_REQUIRE(bytes != nullptr, "bytes == NULL");
     const int64_t n_mtiles = (n_qtok + BM - 1) / BM;
