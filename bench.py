@@ -318,6 +318,10 @@ def run_ours(args):
     assert np.array_equal(vals, res["_bootstrap_values"]), "device-resident step and API step disagree"
 
     pk = peaks()
+    traffic = None      # DRAM bytes per launch from the committed ncu --set full capture (only valid at N=1 shapes)
+    tp = ROOT / "profiles" / "maxsim_ncu_traffic.json"
+    if world == 1 and tp.exists():
+        traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch")
     total_pairs = NQ * ND
     achieved_tf = (NQ * nd_loc * FLOP_PER_PAIR) / (k2_ms * 1e-3) / 1e12          # this rank's K2 launch
     line = {
@@ -339,7 +343,8 @@ def run_ours(args):
                      "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16"],
                      "frac_of_sustained_peak": achieved_tf / pk["bf16_sustained"] if pk["bf16_sustained"] else None,
                      "peak_source": pk["source"] + "; burst cuBLAS figure", "kernel_ms": k2_ms,
-                     "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": NQ * nd_loc, "traffic": None},
+                     "flop_per_pair": FLOP_PER_PAIR, "pairs_per_launch": NQ * nd_loc, "traffic": traffic,
+                     "algorithmic_bytes": (NQ * LQ + nd_loc * LD) * DIM * 2 + NQ * nd_loc * 4},
         "base_recall": {f"R@{k}": v for k, v in ranks.recall().items()},
         "ci": {k: res[k] for k in res if k.startswith("R@")},
     }

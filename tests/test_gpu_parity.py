@@ -401,6 +401,53 @@ def test_run_bootstrap_from_embeddings_vs_oracle(mmx_mod):
     assert [c for c in mmx_mod.CSV_COLUMNS if c not in row] == []
 
 
+def test_run_retrieval_bootstrap_vs_oracle(mmx_mod, monkeypatch):
+    """configs[3]-style protocol (5 caption queries per document, one GT doc each) through the public API from HOST
+    buffers: chunked H2D + K2 + KR + K6 + K3 + K4. Integers vs the numpy multiplicity identity on the GPU's own
+    bitmask, CIs vs the oracle's CI function on the same stream; host-RNG and device-RNG modes must agree exactly."""
+    n_docs, per = 320, 5
+    docs, queries = synth_colpali(n_docs, n_docs * per, doc_len=70, q_len=(6, 14), sigma_q=2.5, seed=12)
+    q2d = np.arange(n_docs * per) // per
+    m_info = {"type": "colpali", "name": "ColSynth"}
+    qv, dv = mmx_mod.FlatMultiVector.from_list(queries), mmx_mod.FlatMultiVector.from_list(docs)
+    B = 50
+    rs = np.random.RandomState(5)
+    res = mmx_mod.run_retrieval_bootstrap(qv, dv, q2d, m_info, B, rng=rs)
+    after = rs.randint(0, 1 << 30)
+    # oracle: scores -> strict-greater sets -> multiplicity identity -> reference CI function, same stream.
+    # (the K2 scores themselves are checked against the oracle elsewhere; using them here keeps near-ties out)
+    S = mmx_mod.compute_similarity_scores(docs, queries, m_info, None)
+    _assert_close_scores(S, oracle.maxsim_scores(queries, docs))
+    gt = [[int(d)] for d in q2d]
+    thr, cnt, _ = oracle.above_gt_counts(S, gt)
+    assert res["base"] == oracle.recall_from_counts(cnt.numpy())
+    rs2 = np.random.RandomState(5)
+    si = rs2.randint(0, n_docs, size=(B, n_docs))
+    above = (S > thr[:, None]).numpy()
+    vals = np.zeros((B, 3))
+    for b in range(B):
+        m = np.bincount(si[b], minlength=n_docs)
+        c = above.astype(np.int64) @ m
+        mq = m[q2d]
+        for j, k in enumerate((1, 5, 10)):
+            vals[b, j] = 100.0 * np.minimum(mq, np.maximum(0, k - c)).sum() / mq.sum()
+    assert np.array_equal(res["_bootstrap_values"], vals)
+    for j, k in enumerate((1, 5, 10)):
+        mean, lo, hi = oracle.bootstrap_confidence_interval(vals[:, j], rng=rs2)
+        assert (res[f"R@{k}_mean"], res[f"R@{k}_lower"], res[f"R@{k}_upper"]) == (mean, lo, hi)
+        assert res[f"R@{k}_std"] == np.std(vals[:, j])
+    assert after == rs2.randint(0, 1 << 30)              # numpy's generator ends where the reference's would
+    # host-drawn random numbers and a single un-chunked upload give the same result
+    monkeypatch.setattr(mmx_mod.api, "DEVICE_RNG", False)
+    monkeypatch.setattr(mmx_mod.api, "H2D_DOC_CHUNKS", 1)
+    res2 = mmx_mod.run_retrieval_bootstrap(queries, docs, q2d, m_info, B, rng=np.random.RandomState(5))
+    for k in res:
+        if isinstance(res[k], np.ndarray):
+            assert np.array_equal(res[k], res2[k])
+        else:
+            assert res[k] == res2[k], k
+
+
 def test_run_bootstrap_colpali_small(mmx_mod):
     """ColPali path end to end on a small ragged problem: base metrics and bootstrap integers vs the oracle."""
     n = 40
