@@ -123,6 +123,19 @@ int mmx_perm_stats(const double* combined, int n1, int n2, const int32_t* perm, 
  * out int32 [count] = the next `count` values numpy would return for randint(0, high). 1 <= high < 2^31. */
 int mmx_mt19937_randint(uint32_t* state, uint32_t high, int64_t count, int32_t* out, cudaStream_t stream);
 
+/* K6p  the same contract, produced by all SMs at once through MT19937 jump-ahead. polys uint32 [n_poly, 624] holds
+ * x^(k * seg_blocks * 624) mod phi(x), k = 1..n_poly (phi = MT19937's characteristic polynomial; the table is built by
+ * multimodal-embedding_b200/mtjump.py): segment k of the stream starts from a GF(2) convolution of the first 33 blocks
+ * with polys[k-1], every CTA regenerates one segment, a count pass and a write pass keep numpy's order under
+ * rejection sampling. Requests beyond one launch's budget are chained; a request that outruns the 2 % slack of its
+ * segment budget is finished by the sequential kernel, so the result never depends on the budget.
+ * scratch: mmx_mt19937_par_scratch_bytes(n_poly). */
+int mmx_mt19937_par_scratch_bytes(int n_poly, size_t* bytes);
+/* Test hook: budget = count / acceptance * rel + blocks * 624 raw words (default 1.02, 64). Results never depend on it. */
+int mmx_mt19937_par_set_slack(double rel, double blocks);
+int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t count, int32_t* out, const uint32_t* polys,
+                            int n_poly, int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

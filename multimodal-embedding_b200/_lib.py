@@ -35,7 +35,10 @@ def _nvcc() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu into csrc/libmmx.so for sm_100a (cross-compiles without a GPU)."""
+    """Compile csrc/*.cu into csrc/libmmx.so for sm_100a (cross-compiles without a GPU) and make sure the MT19937
+    jump-ahead table of K6p (csrc/mt19937_jump_table.npy, ~15 s of host arithmetic once) sits next to it."""
+    from . import mtjump
+    mtjump.load_table(build_if_missing=True)
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     deps = srcs + list(CSRC.glob("*.cuh")) + [_PKG.parent / "include" / "mmx.h"]
     if not force and LIB_PATH.exists():
@@ -98,6 +101,12 @@ _SIGNATURES = {
         _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,   # data, n, idx, R, means, stream
     ]),
     "mmx_mt19937_randint": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p, _c.c_void_p]),
+    "mmx_mt19937_par_scratch_bytes": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_size_t)]),
+    "mmx_mt19937_par_set_slack": (_c.c_int, [_c.c_double, _c.c_double]),
+    "mmx_mt19937_randint_par": (_c.c_int, [
+        _c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p,            # state, high, count, out
+        _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p,   # polys, n_poly, seg_blocks, scratch, bytes, stream
+    ]),
     "mmx_perm_stats": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,  # combined,n1,n2,perm,P,diffs,stream
     ]),

@@ -42,7 +42,7 @@ __device__ __forceinline__ uint32_t temper(uint32_t y) {
 
 __global__ void __launch_bounds__(THREADS, 16)
 mt19937_randint_kernel(uint32_t* __restrict__ state, uint32_t rng, uint32_t mask, long long count,
-                       int32_t* __restrict__ out) {
+                       int32_t* __restrict__ out, const unsigned long long* __restrict__ seg_cnt, int n_seg) {
     __shared__ uint32_t key[2][N];
     __shared__ int round_cnt[32];
     __shared__ int new_pos_s;
@@ -53,6 +53,10 @@ mt19937_randint_kernel(uint32_t* __restrict__ state, uint32_t rng, uint32_t mask
     int pos = (int)state[N];
     int cur = 0;
     long long produced = 0;
+    // tail of the parallel path: the segments already emitted sum(seg_cnt) values; nothing to do unless the
+    // budgeted stream ran out early (then `state` is the end of the last segment and the loop simply continues)
+    for (int j = 0; j < n_seg; ++j) produced += (long long)seg_cnt[j];
+    if (produced >= count) return;
     __syncthreads();
     while (produced < count) {
         if (pos >= N) {
@@ -145,7 +149,326 @@ extern "C" int mmx_mt19937_randint(uint32_t* state, uint32_t high, int64_t count
     mask |= mask >> 4;
     mask |= mask >> 8;
     mask |= mask >> 16;
-    rng::mt19937_randint_kernel<<<1, rng::THREADS, 0, stream>>>(state, r, mask, (long long)count, out);
+    rng::mt19937_randint_kernel<<<1, rng::THREADS, 0, stream>>>(state, r, mask, (long long)count, out, nullptr, 0);
     MMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+
+// ================================================================================================================
+// K6p — the same stream, produced by every SM at once (MT19937 jump-ahead).
+//
+// The stream is cut into segments of `seg_blocks` numpy blocks (624 raw words each); segment k starts from the block
+// W_k = F^(k * seg_blocks * 624)(key), obtained WITHOUT stepping: MT19937 is a linear recurrence over GF(2) with a
+// degree-19937 characteristic polynomial phi, so with g_k(x) = x^(k*seg_words) mod phi(x) (host table,
+// multimodal-embedding_b200/mtjump.py) every raw word obeys x[n + k*seg_words] = XOR_{i: g_k[i]=1} x[n + i]:
+// W_k is a GF(2) convolution of the first 33 blocks of the stream (expanded once by one CTA) with the bits of g_k.
+// Then every CTA regenerates its own segment. Two passes keep numpy's order under rejection sampling: pass A counts
+// the accepted values per segment, pass B recomputes them and writes at the prefix-summed offsets; the CTA that
+// emits the last requested value stores the generator state (block key + position) exactly where numpy would be.
+// The segment budget carries 2 % + 64 blocks of slack over the expected rejection rate; should a request still
+// outrun it, the sequential kernel above finishes the remainder in the same stream order (no host round trip).
+// ================================================================================================================
+namespace mmx {
+namespace rng {
+
+constexpr int PTHREADS = 256;
+constexpr int PWARPS = PTHREADS / 32;
+constexpr int XBLOCKS = 33;  // 33 * 624 = 20592 >= 19937 + 623 raw words feed the convolution
+
+struct ParParams {
+    const uint32_t* state;        // [625] key + pos (read only)
+    const uint32_t* polys;        // [n_poly][624] jump polynomials, polys[k-1] = x^(k*seg_words) mod phi
+    uint32_t* xstream;            // [XBLOCKS * 624] raw words that follow the current key (key itself = block 0)
+    uint32_t* seg_states;         // [n_seg][624]
+    unsigned long long* seg_cnt;  // [n_seg]
+    uint32_t* state_out;          // [625] key + pos where the request ends
+    int32_t* out;
+    long long count;
+    int n_seg, seg_blocks;
+    uint32_t rng, mask;
+};
+
+// n = the block after o (both in shared memory), 256 threads
+__device__ __forceinline__ void gen_block256(const uint32_t* o, uint32_t* n, int t) {
+    if (t < 227) n[t] = o[t + M] ^ twist(o[t], o[t + 1]);
+    __syncthreads();
+    if (t < 227) n[t + 227] = n[t] ^ twist(o[t + 227], o[t + 228]);
+    __syncthreads();
+    if (t < 169) n[t + 454] = n[t + 227] ^ twist(o[t + 454], o[t + 455]);
+    if (t == 255) n[623] = n[396] ^ twist(o[623], n[0]);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PTHREADS)
+mt_par_expand_kernel(const ParParams p) {
+    __shared__ uint32_t key[2][N];
+    const int t = threadIdx.x;
+    for (int i = t; i < N; i += PTHREADS) {
+        key[0][i] = p.state[i];
+        p.xstream[i] = key[0][i];
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int b = 1; b < XBLOCKS; ++b) {
+        gen_block256(key[cur], key[cur ^ 1], t);
+        cur ^= 1;
+        for (int i = t; i < N; i += PTHREADS) p.xstream[b * N + i] = key[cur][i];
+    }
+}
+
+__global__ void __launch_bounds__(PTHREADS)
+mt_par_count_kernel(const ParParams p) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* x = sm;                   // [XBLOCKS * N] raw stream from the base key (segments k > 0)
+    uint32_t* key0 = sm + XBLOCKS * N;  // two block buffers for the segment itself
+    uint32_t* key1 = key0 + N;
+    __shared__ unsigned long long wcnt[PWARPS];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int k = blockIdx.x;
+    const int pos0 = (int)p.state[N];
+    if (k == 0) {
+        for (int i = t; i < N; i += PTHREADS) key0[i] = p.state[i];
+    } else {
+        for (int i = t; i < XBLOCKS * N; i += PTHREADS) x[i] = p.xstream[i];
+        __syncthreads();
+        const uint32_t* g = p.polys + (size_t)(k - 1) * N;
+        uint32_t a0 = 0, a1 = 0, a2 = 0;
+        const bool third = t + 512 < N;
+        const uint32_t* xt = x + t;
+        uint32_t gnext = __ldg(g);
+        for (int w = 0; w < N; ++w) {
+            uint32_t gw = gnext;
+            if (w + 1 < N) gnext = __ldg(g + w + 1);
+            const uint32_t* xw = xt + w * 32;
+            while (gw) {
+                const int i = __ffs(gw) - 1;
+                gw &= gw - 1;
+                a0 ^= xw[i];
+                a1 ^= xw[i + 256];
+                if (third) a2 ^= xw[i + 512];
+            }
+        }
+        key0[t] = a0;
+        key0[t + 256] = a1;
+        if (third) key0[t + 512] = a2;
+    }
+    __syncthreads();
+    for (int i = t; i < N; i += PTHREADS) p.seg_states[(size_t)k * N + i] = key0[i];
+    // ---- count the accepted values of this segment (segment 0: plus the unread tail of the current block)
+    unsigned long long cnt = 0;
+    if (k == 0) {
+        for (int e = t; e < N; e += PTHREADS)
+            if (e >= pos0 && (temper(key0[e]) & p.mask) <= p.rng) ++cnt;
+    }
+    uint32_t* o = key0;
+    uint32_t* n = key1;
+    for (int b = 0; b < p.seg_blocks; ++b) {
+        gen_block256(o, n, t);
+        for (int e = t; e < N; e += PTHREADS)
+            if ((temper(n[e]) & p.mask) <= p.rng) ++cnt;
+        uint32_t* tmp = o;
+        o = n;
+        n = tmp;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    if (lane == 0) wcnt[warp] = cnt;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long tot = 0;
+        for (int w = 0; w < PWARPS; ++w) tot += wcnt[w];
+        p.seg_cnt[k] = tot;
+    }
+}
+
+// pass B: ordered compaction of the accepted words of the segment at the prefix-summed offset
+__global__ void __launch_bounds__(PTHREADS)
+mt_par_write_kernel(const ParParams p) {
+    __shared__ uint32_t key[2][N];
+    __shared__ int round_cnt[32];
+    __shared__ int stop_pos_s;
+    __shared__ unsigned long long base_s, total_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int k = blockIdx.x;
+    if (t < 32) {
+        round_cnt[t] = 0;
+        unsigned long long b = 0, tot = 0;
+        for (int j = lane; j < p.n_seg; j += 32) {
+            const unsigned long long c = p.seg_cnt[j];
+            if (j < k) b += c;
+            tot += c;
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            b += __shfl_xor_sync(0xffffffffu, b, s);
+            tot += __shfl_xor_sync(0xffffffffu, tot, s);
+        }
+        if (lane == 0) {
+            base_s = b;
+            total_s = tot;
+        }
+    }
+    for (int i = t; i < N; i += PTHREADS) key[0][i] = p.seg_states[(size_t)k * N + i];
+    __syncthreads();
+    const long long base = (long long)base_s;
+    const bool shortfall = (long long)total_s < p.count;
+    if (base >= p.count) return;  // the request ends in an earlier segment
+    long long produced = base;    // global index of the next value this CTA emits
+    int cur = 0;
+    int pos = (k == 0) ? (int)p.state[N] : N;
+    int blocks_left = p.seg_blocks;
+    bool finished = false;
+    while (!finished) {
+        if (pos >= N) {
+            if (blocks_left == 0) break;
+            gen_block256(key[cur], key[cur ^ 1], t);
+            cur ^= 1;
+            pos = 0;
+            --blocks_left;
+        }
+        const uint32_t* kk = key[cur];
+        constexpr int RPW8 = (ROUNDS + PWARPS - 1) / PWARPS;  // 3
+        uint32_t v[RPW8], m[RPW8];
+#pragma unroll
+        for (int j = 0; j < RPW8; ++j) {
+            const int r = warp + j * PWARPS;
+            const int e = r * 32 + lane;
+            bool ok = false;
+            v[j] = 0;
+            if (r < ROUNDS && e < N && e >= pos) {
+                v[j] = temper(kk[e]) & p.mask;
+                ok = v[j] <= p.rng;
+            }
+            m[j] = __ballot_sync(0xffffffffu, ok);
+            if (lane == 0 && r < ROUNDS) round_cnt[r] = __popc(m[j]);
+        }
+        __syncthreads();
+        const int c = round_cnt[lane];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const long long need = p.count - produced;
+        const bool last_block = (long long)total >= need;
+#pragma unroll
+        for (int j = 0; j < RPW8; ++j) {
+            const int r = warp + j * PWARPS;
+            const int bs = __shfl_sync(0xffffffffu, incl - c, r & 31);
+            if (r < ROUNDS && ((m[j] >> lane) & 1u)) {
+                const int off = bs + __popc(m[j] & lt);
+                if ((long long)off < need) {
+                    p.out[produced + off] = (int32_t)v[j];
+                    if (last_block && (long long)off == need - 1) stop_pos_s = r * 32 + lane + 1;
+                }
+            }
+        }
+        __syncthreads();
+        if (last_block) {
+            pos = stop_pos_s;
+            finished = true;
+        } else {
+            pos = N;
+            produced += total;
+        }
+    }
+    if (finished || (shortfall && k == p.n_seg - 1)) {
+        // this CTA emitted the last requested value (or the budgeted stream ended): numpy's state is here
+        for (int i = t; i < N; i += PTHREADS) p.state_out[i] = key[cur][i];
+        if (t == 0) p.state_out[N] = (uint32_t)pos;
+    }
+}
+
+static uint32_t mask_of(uint32_t r) {
+    uint32_t mask = r;
+    mask |= mask >> 1;
+    mask |= mask >> 2;
+    mask |= mask >> 4;
+    mask |= mask >> 8;
+    mask |= mask >> 16;
+    return mask;
+}
+
+// raw words a request for `count` accepted values is budgeted with (mmx_mt19937_par_set_slack: test hook that
+// lets the parity tests starve the budget and exercise the sequential finish)
+static double g_slack_rel = 1.02, g_slack_blocks = 64.0;
+static double budget_words(uint32_t r, double count) {
+    const double p = ((double)r + 1.0) / ((double)mask_of(r) + 1.0);
+    return count / p * g_slack_rel + g_slack_blocks * N;
+}
+
+}  // namespace rng
+}  // namespace mmx
+
+extern "C" int mmx_mt19937_par_set_slack(double rel, double blocks) {
+    MMX_REQUIRE(rel > 0.0 && blocks >= 0.0, "bad slack");
+    mmx::rng::g_slack_rel = rel;
+    mmx::rng::g_slack_blocks = blocks;
+    return 0;
+}
+
+extern "C" int mmx_mt19937_par_scratch_bytes(int n_poly, size_t* bytes) {
+    MMX_REQUIRE(bytes != nullptr && n_poly >= 1, "bad argument");
+    using namespace mmx::rng;
+    *bytes = (size_t)XBLOCKS * N * 4 + (size_t)(n_poly + 1) * N * 4 + (size_t)(n_poly + 1) * 8 + 625 * 4 + 1024;
+    return 0;
+}
+
+extern "C" int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t count, int32_t* out,
+                                       const uint32_t* polys, int n_poly, int seg_blocks, void* scratch,
+                                       size_t scratch_bytes, cudaStream_t stream) {
+    using namespace mmx::rng;
+    MMX_REQUIRE(state != nullptr && (out != nullptr || count == 0) && polys != nullptr && scratch != nullptr,
+                "NULL argument");
+    MMX_REQUIRE(high >= 1 && high <= 0x7fffffffu, "high must be in [1, 2^31)");
+    MMX_REQUIRE(count >= 0 && n_poly >= 1 && seg_blocks >= 1, "bad argument");
+    if (count == 0 || high == 1) return mmx_mt19937_randint(state, high, count, out, stream);
+    size_t need = 0;
+    mmx_mt19937_par_scratch_bytes(n_poly, &need);
+    MMX_REQUIRE(scratch_bytes >= need, "scratch too small: need %zu bytes", need);
+    ParParams p;
+    uintptr_t ws = (reinterpret_cast<uintptr_t>(scratch) + 255) & ~uintptr_t(255);
+    p.xstream = reinterpret_cast<uint32_t*>(ws);
+    ws += (size_t)XBLOCKS * N * 4;
+    p.seg_states = reinterpret_cast<uint32_t*>(ws);
+    ws += (size_t)(n_poly + 1) * N * 4;
+    p.seg_cnt = reinterpret_cast<unsigned long long*>(ws);
+    ws += (size_t)(n_poly + 1) * 8;
+    p.state_out = reinterpret_cast<uint32_t*>(ws);
+    p.state = state;
+    p.polys = polys;
+    p.seg_blocks = seg_blocks;
+    p.rng = high - 1;
+    p.mask = mask_of(p.rng);
+    const size_t smem = (size_t)(XBLOCKS + 2) * N * 4;
+    MMX_CHECK_CUDA(cudaFuncSetAttribute(mt_par_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const double per_seg = (double)seg_blocks * N;
+    // values one launch (n_poly + 1 segments) is budgeted to deliver; larger requests are chained launches, each
+    // continuing from the state the previous one left (stream order)
+    const double cap_words = per_seg * (n_poly + 1);
+    MMX_REQUIRE(cap_words > 128.0 * N, "jump table too small");
+    const double accept = ((double)p.rng + 1.0) / ((double)p.mask + 1.0);
+    const int64_t cap_count = (int64_t)((cap_words - 64.0 * N) / 1.02 * accept);  // default slack: chunking is fixed
+    int64_t done = 0;
+    while (done < count) {
+        const int64_t c = (count - done < cap_count) ? (count - done) : cap_count;
+        int n_seg = (int)(budget_words(p.rng, (double)c) / per_seg) + 1;
+        if (n_seg > n_poly + 1) n_seg = n_poly + 1;
+        p.out = out + done;
+        p.count = c;
+        p.n_seg = n_seg;
+        mt_par_expand_kernel<<<1, PTHREADS, 0, stream>>>(p);
+        mt_par_count_kernel<<<n_seg, PTHREADS, smem, stream>>>(p);
+        mt_par_write_kernel<<<n_seg, PTHREADS, 0, stream>>>(p);
+        MMX_CHECK_CUDA(cudaGetLastError());
+        MMX_CHECK_CUDA(cudaMemcpyAsync(state, p.state_out, 625 * 4, cudaMemcpyDeviceToDevice, stream));
+        mt19937_randint_kernel<<<1, THREADS, 0, stream>>>(state, p.rng, p.mask, (long long)c, p.out, p.seg_cnt, n_seg);
+        MMX_CHECK_CUDA(cudaGetLastError());
+        done += c;
+    }
     return 0;
 }

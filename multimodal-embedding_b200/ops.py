@@ -233,6 +233,9 @@ class DeviceRng:
     ``choice(data, n)`` draws of main.py:588,269) as a CUDA int32 tensor; ``commit()`` writes the advanced state back
     into the numpy object, so the host stream continues as if numpy itself had made the draws."""
 
+    PAR_MIN_COUNT = 200_000      # below this one small CTA (K6) is as fast as the jump-ahead launch sequence (K6p)
+    _tables: dict = {}           # device -> (polys tensor, scratch tensor)
+
     def __init__(self, source, device: Optional[torch.device] = None):
         self.source = np.random if source is None else source
         st = self.source.get_state()
@@ -242,10 +245,31 @@ class DeviceRng:
         host = np.concatenate([np.asarray(st[1], dtype=np.uint32), np.array([st[2]], dtype=np.uint32)])
         self.state = torch.from_numpy(host.view(np.int32).copy()).to(dev)
 
-    def randint(self, high: int, count: int) -> torch.Tensor:
+    def _par_buffers(self):
+        dev = self.state.device
+        if dev not in DeviceRng._tables:
+            from . import mtjump
+            polys = torch.from_numpy(mtjump.load_table(build_if_missing=False).view(np.int32)).to(dev)
+            need = ctypes.c_size_t()
+            _lib.check(_lib.lib().mmx_mt19937_par_scratch_bytes(mtjump.N_POLY, ctypes.byref(need)))
+            DeviceRng._tables[dev] = (polys, torch.empty(need.value, dtype=torch.uint8, device=dev))
+        return DeviceRng._tables[dev]
+
+    def randint(self, high: int, count: int, parallel: Optional[bool] = None) -> torch.Tensor:
+        """The next `count` values of ``randint(0, high)``. Large requests use the jump-ahead kernels (K6p, all SMs),
+        small ones the single-CTA kernel (K6); both continue the same stream, so they can be mixed freely."""
         out = torch.empty((count,), dtype=torch.int32, device=self.state.device)
-        _lib.check(_lib.lib().mmx_mt19937_randint(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
-                                                  _stream()))
+        if parallel is None:
+            parallel = count >= self.PAR_MIN_COUNT
+        if parallel:
+            from . import mtjump
+            polys, scratch = self._par_buffers()
+            _lib.check(_lib.lib().mmx_mt19937_randint_par(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
+                                                          polys.data_ptr(), mtjump.N_POLY, mtjump.SEG_BLOCKS,
+                                                          scratch.data_ptr(), scratch.numel(), _stream()))
+        else:
+            _lib.check(_lib.lib().mmx_mt19937_randint(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
+                                                      _stream()))
         return out
 
     def commit(self) -> None:

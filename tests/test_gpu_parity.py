@@ -347,6 +347,43 @@ def test_device_rng_matches_numpy_stream(mmx_mod, high):
     assert rs_dev.randint(0, 1 << 30) == rs_ref.randint(0, 1 << 30)
 
 
+@pytest.mark.parametrize("high,count", [(2, 300_000), (1000, 10_000_000), (5000, 5_000_000), (5001, 700_001),
+                                        (25000, 2_000_003), ((1 << 31) - 1, 1_000_000), (1000, 30_000_000)])
+def test_device_rng_jump_ahead_matches_numpy_stream(mmx_mod, high, count):
+    """K6p (MT19937 jump-ahead, one CTA per 64-block segment, chained launches for the 3e7 request): identical values,
+    identical generator state, mixable with the single-CTA kernel and with host draws."""
+    rs_dev, rs_ref = np.random.RandomState(99), np.random.RandomState(99)
+    for r in (rs_dev, rs_ref):
+        r.randint(0, 13, size=700)                        # position 700 % 624 inside a block
+    d = mmx_mod.ops.DeviceRng(rs_dev)
+    a = d.randint(high, count, parallel=True)
+    b = d.randint(high, 1000, parallel=False)             # sequential kernel continues from the jump-ahead state
+    c = d.randint(high, 250_000, parallel=True)
+    d.commit()
+    for got, n in ((a, count), (b, 1000), (c, 250_000)):
+        want = rs_ref.randint(0, high, size=n)
+        assert np.array_equal(got.cpu().numpy().astype(np.int64), want)
+    sa, sb = rs_dev.get_state(), rs_ref.get_state()
+    assert np.array_equal(sa[1], sb[1]) and sa[2:] == sb[2:]
+    assert rs_dev.randint(0, 1 << 30) == rs_ref.randint(0, 1 << 30)
+
+
+def test_device_rng_jump_ahead_starved_budget(mmx_mod):
+    """A request that outruns its segment budget (forced here by shrinking the slack) is finished by the sequential
+    kernel in stream order: same values, same state."""
+    h = mmx_mod._lib.lib()
+    try:
+        mmx_mod._lib.check(h.mmx_mt19937_par_set_slack(0.80, 0.0))
+        rs_dev, rs_ref = np.random.RandomState(7), np.random.RandomState(7)
+        d = mmx_mod.ops.DeviceRng(rs_dev)
+        got = d.randint(5000, 1_000_000, parallel=True).cpu().numpy()
+        d.commit()
+    finally:
+        mmx_mod._lib.check(h.mmx_mt19937_par_set_slack(1.02, 64.0))
+    assert np.array_equal(got.astype(np.int64), rs_ref.randint(0, 5000, size=1_000_000))
+    assert rs_dev.randint(0, 1 << 30) == rs_ref.randint(0, 1 << 30)
+
+
 def test_device_rng_global_stream_and_host_mode_agree(mmx_mod, golden_dir, monkeypatch):
     """bootstrap_confidence_interval on the GLOBAL np.random stream: device-drawn (default) and host-drawn index
     streams give the same tuple and leave np.random in the same state as the reference's 10 000 choice() calls."""
