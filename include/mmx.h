@@ -83,6 +83,29 @@ int mmx_rank_from_scores(const float* scores, int64_t nq, int64_t ng, int64_t ld
                          uint32_t* above_bits, int64_t words_per_row, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * KT  per-query top-k lists — the `torch.topk(scores[i], k)` of main.py:333,362,372 (v28 :211,222) itself, for callers
+ * that want the retrieved items and for the multi-GPU merge. Order: higher score first, ties by lower column index
+ * (torch leaves tied order unspecified, tie class T2). top_s fp32 [nq, k], top_i int32 [nq, k] hold GLOBAL column ids
+ * (g_base + local column); rows with fewer than k columns are padded with (-inf, -1). 1 <= k <= 32.
+ *   mmx_topk_from_scores  one pass over a materialised fp32 matrix (what K2 produces).
+ *   mmx_dense_topk        K1 without the matrix: a group-maximum pass bounds every row's k-th score, a second pass
+ *                         collects the few candidates above that bound, a warp picks the k best.
+ *                         workspace: mmx_dense_topk_workspace_bytes(nq, ng).
+ *   mmx_topk_select       best k of per-row candidate lists cand_s/cand_i [nq, cap] (cand_n nullable [nq] = valid
+ *                         entries per row; negative indices are padding).
+ *   mmx_merge_topk        gathered per-shard lists, laid out [nq, n_shards * k], -> global top-k.
+ */
+int mmx_topk_from_scores(const float* scores, int64_t nq, int64_t ng, int64_t ld, int64_t g_base, int k, float* top_s,
+                         int32_t* top_i, cudaStream_t stream);
+int mmx_dense_topk_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes);
+int mmx_dense_topk(const void* Q, int64_t nq, const void* G, int64_t ng, int d, int64_t g_base, int k, float* top_s,
+                   int32_t* top_i, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+int mmx_topk_select(const float* cand_s, const int32_t* cand_i, const int32_t* cand_n, int64_t nq, int cap, int k,
+                    float* top_s, int32_t* top_i, cudaStream_t stream);
+int mmx_merge_topk(const float* gathered_s, const int32_t* gathered_i, int n_shards, int64_t nq, int k, float* top_s,
+                   int32_t* top_i, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * K3  bootstrap — replaces the resample/gather/rescore/metrics loop of main.py:586-634 by the multiplicity
  * identity of SURVEY 5.4 on the BASE score pass:
  *     m = bincount(sample_indices[b]);  c_q = sum_col m[col2unit[col]] * above[q, col];

@@ -16,7 +16,7 @@ from typing import Optional
 _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 LIB_PATH = CSRC / "libmmx.so"
-SOURCES = ["mmx_host.cu", "maxsim.cu", "dense_rank.cu", "rank_scores.cu", "stats.cu", "rng.cu"]
+SOURCES = ["mmx_host.cu", "maxsim.cu", "dense_rank.cu", "rank_scores.cu", "topk.cu", "stats.cu", "rng.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -85,6 +85,23 @@ _SIGNATURES = {
         _c.c_void_p, _c.c_void_p, _c.c_int64,                         # gt_off, gt_idx, g_base
         _c.c_int, _c.c_void_p,                                        # mode, thr
         _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p,            # cnt_above, above_bits, words_per_row, stream
+    ]),
+    "mmx_topk_from_scores": (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,    # scores, nq, ng, ld, g_base, k
+        _c.c_void_p, _c.c_void_p, _c.c_void_p,                                    # top_s, top_i, stream
+    ]),
+    "mmx_dense_topk_workspace_bytes": (_c.c_int, [_c.c_int64, _c.c_int64, _c.POINTER(_c.c_size_t)]),
+    "mmx_dense_topk": (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int64, _c.c_int,   # Q, nq, G, ng, d, g_base, k
+        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p,                    # top_s, top_i, ws, bytes, stream
+    ]),
+    "mmx_topk_select": (_c.c_int, [
+        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int,    # cand_s, cand_i, cand_n, nq, cap, k
+        _c.c_void_p, _c.c_void_p, _c.c_void_p,                                    # top_s, top_i, stream
+    ]),
+    "mmx_merge_topk": (_c.c_int, [
+        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int,                 # gathered_s, gathered_i, n_shards, nq, k
+        _c.c_void_p, _c.c_void_p, _c.c_void_p,                                    # top_s, top_i, stream
     ]),
     "mmx_bincount": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,  # idx,B,n_draws,n_units,scratch,mult,stream

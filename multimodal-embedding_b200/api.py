@@ -251,13 +251,14 @@ def permutation_test(data1: np.ndarray, data2: np.ndarray, n_permutations: int =
 
 # ------------------------------------------------------------------------------------------------ fused path
 def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, caps_per_img: int = 5,
-                   want_bits: bool = True) -> Dict[str, ops.ProtocolRanks]:
+                   want_bits: bool = True, want_top10: bool = False) -> Dict[str, ops.ProtocolRanks]:
     """One scoring pass over the BASE embeddings for the three protocols of run_bootstrap_benchmark
     (main.py:599-624 GT structure: query i <-> image i, image i <-> captions [5i, 5i+5)).
 
     Dense models never materialise a score matrix (K1). ColPali writes the final [n_q, n_doc] fp32 scores (one float
     per 5.3 MFLOP pair) and ranks them with KR; I2T uses images as MaxSim queries (v28 :375-386) and I2T_Sym the
-    transposed T2I matrix exactly as main.py:624."""
+    transposed T2I matrix exactly as main.py:624. ``want_top10`` also fills ``top_s`` / ``top_i`` of every protocol with
+    the retrieved items (`torch.topk(row, 10)` of main.py:333,362,372) — still without a dense score matrix."""
     dev = _device()
     out: Dict[str, ops.ProtocolRanks] = {}
     if m_info["type"] == "colpali":
@@ -273,7 +274,11 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
         b_off, b_idx = _block_gt(n, caps_per_img, dev)
         out["T2I"] = ops.rank_from_scores(s_t2i, id_off, id_idx, want_bits)
         out["I2T"] = ops.rank_from_scores(s_i2t, b_off, b_idx, want_bits)
-        out["I2T_Sym"] = ops.rank_from_scores(s_t2i.t().contiguous(), id_off, id_idx, want_bits)
+        s_sym = s_t2i.t().contiguous()
+        out["I2T_Sym"] = ops.rank_from_scores(s_sym, id_off, id_idx, want_bits)
+        if want_top10:
+            for name, sc in (("T2I", s_t2i), ("I2T", s_i2t), ("I2T_Sym", s_sym)):
+                out[name].top_s, out[name].top_i = ops.topk_from_scores(sc, 10)
     else:
         img = _h2d(_as_bf16(img_embeds, "img_embeds"), dev)
         t2i = _h2d(_as_bf16(t2i_txt_embeds, "t2i_txt_embeds"), dev)
@@ -284,6 +289,9 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
         out["T2I"] = ops.dense_rank(t2i, img, id_off, id_idx, want_bits)         # [n_txt, n_img]   main.py:620
         out["I2T"] = ops.dense_rank(img, allc, b_off, b_idx, want_bits)          # [n_img, 5 n_img] main.py:622 (D1 fixed)
         out["I2T_Sym"] = ops.dense_rank(img, t2i, id_off, id_idx, want_bits)     # = scores_t2i.t() main.py:624
+        if want_top10:
+            for name, (qq, gg) in (("T2I", (t2i, img)), ("I2T", (img, allc)), ("I2T_Sym", (img, t2i))):
+                out[name].top_s, out[name].top_i = ops.dense_topk(qq, gg, 10)
     out["I2T"].col2unit = torch.arange(n * caps_per_img, dtype=torch.int32, device=dev) // caps_per_img
     return out
 

@@ -8,15 +8,24 @@
 //   MODE_THRESHOLD  only tiles that hold a GT column; epilogue: thr[q] = max(thr[q], S[q, c]) for c in GT(q)
 //   MODE_COUNT      every tile; epilogue: bits = (S[q, :] > thr[q]) packed 32 columns per word, cnt_above += popc,
 //                   optionally the fp32 scores themselves (the drop-in compute_similarity_scores needs them).
+// Top-k without the matrix (mmx_dense_topk) is two more uses of the same code: MODE_GROUPMAX stores the maximum of
+// every 32-column group (256 for huge galleries) per query; the k-th largest group maximum t_k of a row is a lower
+// bound of its k-th largest score (k groups hold a value >= t_k), so a COUNT pass with the bar at t_k meets only a
+// handful of candidates per row (k plus the few extra values sharing a group) and appends them (score, column) to a
+// short per-row list, from which a warp picks the final k.
 //
 // CTA = persistent worker over 128 x 256 output tiles; K streams through a 4-stage TMA ring in 64-wide
 // (128-byte, swizzled) blocks; accumulators ping-pong between TMEM columns [0,256) and [256,512) so the epilogue
 // of tile t overlaps the MMAs of tile t+1. Warp roles: 0 = TMA, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
 #include <cfloat>
+#include <cuda_bf16.h>
 
 #include "../../include/mmx.h"
 #include "mmx_host.cuh"
 #include "sm100_ptx.cuh"
+#include "topk.cuh"
+
+#define MMX_MODE_GROUPMAX 2   // internal to mmx_dense_topk
 
 namespace mmx {
 namespace dense {
@@ -40,6 +49,13 @@ struct Params {
     long long ld_scores;
     const int32_t* tile_list;   // MODE_THRESHOLD: compacted ids of tiles holding a GT column
     const int32_t* n_tiles_dev; // MODE_THRESHOLD: their count (device scalar)
+    float* grp_max;             // MODE_GROUPMAX: [nq, n_grp] maxima of 32-column groups (grp_tile: of 256-column tiles)
+    long long n_grp;
+    int grp_tile;
+    float* cand_s;              // MODE_COUNT, optional: scores above thr are appended to a per-row candidate list
+    int32_t* cand_i;            //   [nq, cand_cap] global column ids; cand_n [nq] counts every hit (may exceed the cap)
+    int32_t* cand_n;
+    int cand_cap;
     long long nq, ng;
     int kblocks, n_mblk, n_ntile, n_tiles, mode;
 };
@@ -70,6 +86,9 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
         atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// MODE is a template parameter: each pass gets an epilogue without the other passes' code (the threshold pass
+// indexes the accumulator registers dynamically, which would put the COUNT pass's registers on the stack too).
+template <int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                   const __grid_constant__ Params p) {
@@ -156,9 +175,9 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             // per-row state, loaded while the MMAs of this tile are still running
             float thr = INFINITY;
             int e0 = 0, e1 = 0;
-            if (p.mode == MMX_MODE_COUNT) {
+            if (MODE == MMX_MODE_COUNT) {
                 if (valid_row) thr = __ldg(p.thr + q);
-            } else if (valid_row) {
+            } else if (MODE == MMX_MODE_THRESHOLD && valid_row) {
                 e0 = __ldg(p.gt_off + q);
                 e1 = __ldg(p.gt_off + q + 1);
             }
@@ -172,7 +191,16 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 tmem_ld_32x32(taddr + ch * 32, v);
                 tmem_ld_wait();
                 const long long c0 = n0 + ch * 32;
-                if (p.mode == MMX_MODE_COUNT) {
+                if (MODE == MMX_MODE_GROUPMAX) {
+                    const long long nvalid = p.ng - c0;
+                    float m = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) m = fmaxf(m, j < nvalid ? __uint_as_float(v[j]) : -INFINITY);
+                    if (p.grp_tile)
+                        best = fmaxf(best, m);
+                    else if (valid_row && nvalid > 0)
+                        p.grp_max[q * p.n_grp + (c0 >> 5)] = m;
+                } else if (MODE == MMX_MODE_COUNT) {
                     const long long nvalid = p.ng - c0;
                     const uint32_t cmask = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << (int)nvalid) - 1u));
                     uint32_t bits = 0;
@@ -183,6 +211,18 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     const long long w = (c0 >> 5);
                     if (p.above_bits != nullptr && valid_row && w < p.words_per_row)
                         p.above_bits[q * p.words_per_row + w] = bits;
+                    if (p.cand_n != nullptr && bits != 0u && valid_row) {   // rare: a handful of hits per row in total
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if ((bits >> j) & 1u) {
+                                const int slot = atomicAdd(p.cand_n + q, 1);
+                                if (slot < p.cand_cap) {
+                                    p.cand_s[q * p.cand_cap + slot] = __uint_as_float(v[j]);
+                                    p.cand_i[q * p.cand_cap + slot] = (int32_t)(p.g_base + c0 + j);
+                                }
+                            }
+                        }
+                    }
                     if (p.scores != nullptr && valid_row) {
                         float* dst = p.scores + q * p.ld_scores + c0;
                         if (nvalid >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -211,8 +251,10 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.t_empty[acc]);
-            if (p.mode == MMX_MODE_COUNT) {
+            if (MODE == MMX_MODE_COUNT) {
                 if (valid_row && cnt > 0) atomicAdd(p.cnt_above + q, cnt);
+            } else if (MODE == MMX_MODE_GROUPMAX) {
+                if (p.grp_tile && valid_row) p.grp_max[q * p.n_grp + n_tile] = best;
             } else if (valid_row && best > -INFINITY) {
                 atomic_max_float(p.thr + q, best);
             }
@@ -255,6 +297,47 @@ extern "C" int mmx_dense_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes) 
     return 0;
 }
 
+static int launch_dense(const void* Q, int64_t nq, const void* G, int64_t ng, int d, const Params& p,
+                        cudaStream_t stream) {
+    CUtensorMap tq, tg;
+    if (make_tmap_bf16_sw128(&tq, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, BM) != 0) return -4;
+    if (make_tmap_bf16_sw128(&tg, G, (uint64_t)ng, (uint64_t)d, (uint64_t)d, BN) != 0) return -4;
+    const size_t smem_bytes = sizeof(Smem) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_THRESHOLD>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_COUNT>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_GROUPMAX>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        attr_set = true;
+    }
+    const int sms = sm_count();
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    if (p.mode == MMX_MODE_COUNT)
+        dense_rank_kernel<MMX_MODE_COUNT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
+    else if (p.mode == MMX_MODE_THRESHOLD)
+        dense_rank_kernel<MMX_MODE_THRESHOLD><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
+    else
+        dense_rank_kernel<MMX_MODE_GROUPMAX><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int base_params(Params& p, int64_t nq, int64_t ng, int d) {
+    const long long n_mblk = (nq + BM - 1) / BM, n_ntile = (ng + BN - 1) / BN;
+    MMX_REQUIRE(n_mblk * n_ntile < (1ll << 31), "too many tiles");
+    p = Params{};
+    p.nq = nq;
+    p.ng = ng;
+    p.kblocks = (d + BK - 1) / BK;
+    p.n_mblk = (int)n_mblk;
+    p.n_ntile = (int)n_ntile;
+    p.n_tiles = (int)(n_mblk * n_ntile);
+    return 0;
+}
+
 extern "C" int mmx_dense_rank(const void* Q, int64_t nq, const void* G, int64_t ng, int d, const int32_t* gt_off,
                               const int32_t* gt_idx, int64_t g_base, int mode, float* thr, int32_t* cnt_above,
                               uint32_t* above_bits, int64_t words_per_row, float* scores, int64_t ld_scores,
@@ -265,9 +348,8 @@ extern "C" int mmx_dense_rank(const void* Q, int64_t nq, const void* G, int64_t 
     MMX_REQUIRE(thr != nullptr, "thr == NULL");
     if (nq == 0 || ng == 0) return 0;
     if (mmx_device_check() != 0) return -3;
-    const long long n_mblk = (nq + BM - 1) / BM, n_ntile = (ng + BN - 1) / BN;
-    MMX_REQUIRE(n_mblk * n_ntile < (1ll << 31), "too many tiles");
     Params p;
+    if (base_params(p, nq, ng, d) != 0) return -2;
     p.gt_off = gt_off;
     p.gt_idx = gt_idx;
     p.g_base = g_base;
@@ -277,14 +359,6 @@ extern "C" int mmx_dense_rank(const void* Q, int64_t nq, const void* G, int64_t 
     p.words_per_row = words_per_row;
     p.scores = scores;
     p.ld_scores = ld_scores;
-    p.tile_list = nullptr;
-    p.n_tiles_dev = nullptr;
-    p.nq = nq;
-    p.ng = ng;
-    p.kblocks = (d + BK - 1) / BK;
-    p.n_mblk = (int)n_mblk;
-    p.n_ntile = (int)n_ntile;
-    p.n_tiles = (int)(n_mblk * n_ntile);
     p.mode = mode;
     if (mode == MMX_MODE_COUNT) {
         MMX_REQUIRE(cnt_above != nullptr, "cnt_above == NULL");
@@ -306,18 +380,157 @@ extern "C" int mmx_dense_rank(const void* Q, int64_t nq, const void* G, int64_t 
         p.tile_list = list;
         p.n_tiles_dev = count;
     }
-    CUtensorMap tq, tg;
-    if (make_tmap_bf16_sw128(&tq, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, BM) != 0) return -4;
-    if (make_tmap_bf16_sw128(&tg, G, (uint64_t)ng, (uint64_t)d, (uint64_t)d, BN) != 0) return -4;
-    const size_t smem_bytes = sizeof(Smem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
-        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        attr_set = true;
+    return launch_dense(Q, nq, G, ng, d, p, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mmx_dense_topk — top-k (score, column) per query without the score matrix
+// ---------------------------------------------------------------------------------------------------------------
+namespace mmx {
+namespace dense {
+
+constexpr int CAND_CAP = 64;           // candidate slots per row; rows that overflow (mass ties) are recomputed exactly
+constexpr int64_t SMALL_GALLERY = 4096;  // below this the matrix is a few KB per row: materialise it in the workspace
+
+// bar[q] = the largest float below the k-th largest group maximum, so that "> bar" means ">= t_k"
+__global__ void __launch_bounds__(256)
+kth_group_bar_kernel(const float* __restrict__ grp_max, long long nq, long long n_grp, int k, float* __restrict__ bar) {
+    const int lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq) return;
+    topk::WarpList L;
+    L.init();
+    const float* row = grp_max + q * n_grp;
+    for (long long c = 0; c < n_grp; c += 32) {
+        const bool ok = c + lane < n_grp;
+        topk::offer(L, ok ? __ldg(row + c + lane) : -INFINITY, (int)(c + lane), ok, k, lane);
     }
-    const int sms = sm_count();
-    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    dense_rank_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
+    if (lane == k - 1) {
+        float t = L.v;  // -inf when the row has fewer than k groups
+        if (t > -INFINITY) t = (t == 0.0f) ? -1.401298464e-45f : __uint_as_float(__float_as_uint(t) + (t > 0.0f ? -1 : 1));
+        bar[q] = t;
+    }
+}
+
+// exact recomputation of the rows whose candidate list overflowed: one warp per row, fp32 dot products
+__global__ void __launch_bounds__(256)
+overflow_rows_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* __restrict__ G, long long nq,
+                     long long ng, int d, long long g_base, const int32_t* __restrict__ cand_n, int k,
+                     float* __restrict__ top_s, int32_t* __restrict__ top_i) {
+    const int lane = threadIdx.x & 31;
+    const long long q = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (q >= nq || __ldg(cand_n + q) <= CAND_CAP) return;
+    topk::WarpList L;
+    L.init();
+    const __nv_bfloat16* qr = Q + q * d;
+    for (long long c = 0; c < ng; c += 32) {
+        const bool ok = c + lane < ng;
+        float acc = 0.0f;
+        if (ok) {
+            const __nv_bfloat16* gr = G + (c + lane) * d;
+            for (int i = 0; i < d; ++i) acc = fmaf(__bfloat162float(qr[i]), __bfloat162float(gr[i]), acc);
+        }
+        topk::offer(L, acc, (int)(c + lane), ok, k, lane);
+    }
+    if (lane < k) {
+        const bool real = L.i != 0x7fffffff;
+        top_s[q * k + lane] = real ? L.v : -INFINITY;
+        top_i[q * k + lane] = real ? (int32_t)(g_base + L.i) : -1;
+    }
+}
+
+struct TopkPlan {
+    bool small;
+    int grp_tile;
+    long long n_grp;
+    size_t off_bar, off_cnt, off_candn, off_cs, off_ci, off_grp, total;
+};
+
+static TopkPlan plan_topk(int64_t nq, int64_t ng) {
+    TopkPlan t{};
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    t.small = ng <= SMALL_GALLERY;
+    size_t o = 256;
+    t.off_bar = o;   o += up((size_t)nq * 4);
+    t.off_cnt = o;   o += up((size_t)nq * 4);
+    if (t.small) {
+        t.off_grp = o; o += up((size_t)nq * (size_t)ng * 4);          // the score matrix itself
+    } else {
+        t.grp_tile = ng > 32768 ? 1 : 0;
+        t.n_grp = t.grp_tile ? (ng + BN - 1) / BN : (ng + 31) / 32;
+        t.off_candn = o; o += up((size_t)nq * 4);
+        t.off_cs = o;    o += up((size_t)nq * CAND_CAP * 4);
+        t.off_ci = o;    o += up((size_t)nq * CAND_CAP * 4);
+        t.off_grp = o;   o += up((size_t)nq * (size_t)t.n_grp * 4);
+    }
+    t.total = o;
+    return t;
+}
+
+}  // namespace dense
+}  // namespace mmx
+
+extern "C" int mmx_dense_topk_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes) {
+    MMX_REQUIRE(bytes != nullptr && nq >= 0 && ng >= 0, "bad argument");
+    *bytes = plan_topk(nq, ng).total;
+    return 0;
+}
+
+extern "C" int mmx_dense_topk(const void* Q, int64_t nq, const void* G, int64_t ng, int d, int64_t g_base, int k,
+                              float* top_s, int32_t* top_i, void* workspace, size_t workspace_bytes,
+                              cudaStream_t stream) {
+    MMX_REQUIRE(nq >= 0 && ng >= 0 && d >= 8 && d % 8 == 0, "bad shape nq=%lld ng=%lld d=%d (d must be a multiple of 8)",
+                (long long)nq, (long long)ng, d);
+    MMX_REQUIRE(k >= 1 && k <= topk::MAX_K, "k must be in [1, %d]", topk::MAX_K);
+    MMX_REQUIRE(top_s != nullptr && top_i != nullptr, "NULL output");
+    MMX_REQUIRE(g_base + ng < (1ll << 31), "column index does not fit int32");
+    if (nq == 0) return 0;
+    if (mmx_device_check() != 0) return -3;
+    const TopkPlan t = plan_topk(nq, ng);
+    MMX_REQUIRE(workspace != nullptr && workspace_bytes >= t.total, "workspace too small: need %zu bytes", t.total);
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    float* bar = reinterpret_cast<float*>(ws + t.off_bar);
+    int32_t* cnt = reinterpret_cast<int32_t*>(ws + t.off_cnt);
+    Params p;
+    if (ng == 0) return mmx_topk_from_scores(nullptr, nq, 0, 0, g_base, k, top_s, top_i, stream);
+    if (base_params(p, nq, ng, d) != 0) return -2;
+    p.g_base = g_base;
+    p.thr = bar;
+    p.cnt_above = cnt;
+    if (t.small) {
+        // bar = +inf: nothing counts, the epilogue only stores the scores
+        float* S = reinterpret_cast<float*>(ws + t.off_grp);
+        MMX_CHECK_CUDA(cudaMemsetAsync(bar, 0x7f, (size_t)nq * 4, stream));   // 0x7f7f7f7f = 3.39e38 > any score
+        p.mode = MMX_MODE_COUNT;
+        p.scores = S;
+        p.ld_scores = ng;
+        if (int rc = launch_dense(Q, nq, G, ng, d, p, stream)) return rc;
+        return mmx_topk_from_scores(S, nq, ng, ng, g_base, k, top_s, top_i, stream);
+    }
+    float* grp = reinterpret_cast<float*>(ws + t.off_grp);
+    int32_t* cand_n = reinterpret_cast<int32_t*>(ws + t.off_candn);
+    float* cand_s = reinterpret_cast<float*>(ws + t.off_cs);
+    int32_t* cand_i = reinterpret_cast<int32_t*>(ws + t.off_ci);
+    p.mode = MMX_MODE_GROUPMAX;
+    p.grp_max = grp;
+    p.n_grp = t.n_grp;
+    p.grp_tile = t.grp_tile;
+    if (int rc = launch_dense(Q, nq, G, ng, d, p, stream)) return rc;
+    kth_group_bar_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(grp, nq, t.n_grp, k, bar);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    MMX_CHECK_CUDA(cudaMemsetAsync(cand_n, 0, (size_t)nq * 4, stream));
+    MMX_CHECK_CUDA(cudaMemsetAsync(cnt, 0, (size_t)nq * 4, stream));
+    p.mode = MMX_MODE_COUNT;
+    p.grp_max = nullptr;
+    p.cand_s = cand_s;
+    p.cand_i = cand_i;
+    p.cand_n = cand_n;
+    p.cand_cap = CAND_CAP;
+    if (int rc = launch_dense(Q, nq, G, ng, d, p, stream)) return rc;
+    if (int rc = mmx_topk_select(cand_s, cand_i, cand_n, nq, CAND_CAP, k, top_s, top_i, stream)) return rc;
+    overflow_rows_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(Q), reinterpret_cast<const __nv_bfloat16*>(G), nq, ng, d, g_base, cand_n,
+        k, top_s, top_i);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -7,7 +7,8 @@ bootstrap the per-query hit totals come from K3 (``q_hits1``) instead of 5 000 0
 from __future__ import annotations
 
 from collections import defaultdict
-from typing import Any, Dict, List, Optional, Sequence
+from functools import lru_cache
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -36,24 +37,36 @@ LENGTH_BINS = [(0, 5), (6, 10), (11, 15), (16, 100)]                            
 FEATURES = ["has_spatial", "has_color", "has_counting"]
 
 
+def _contains_any(text: str, keywords: Sequence[str]) -> bool:
+    for kw in keywords:
+        if kw in text:
+            return True
+    return False
+
+
+@lru_cache(maxsize=1 << 17)
+def _caption_features(caption: str) -> Tuple[bool, bool, bool, int, Optional[str]]:
+    """(has_spatial, has_color, has_counting, length, category) of one caption. Memoised: the reference recomputes
+    these for every (iteration, query) record — 5 000 000 times per model — and every model sees the same captions."""
+    text = caption.lower()
+    category = None
+    for name, keywords in COCO_SUPERCATEGORIES.items():
+        if _contains_any(text, keywords):
+            category = name
+            break
+    return (_contains_any(text, SPATIAL_KEYWORDS), _contains_any(text, COLOR_KEYWORDS),
+            _contains_any(text, COUNTING_KEYWORDS), len(caption.split()), category)
+
+
 def analyze_query_complexity(caption: str) -> Dict[str, Any]:
     """main.py:239-247."""
-    text = caption.lower()
-    return {
-        "has_spatial": any(kw in text for kw in SPATIAL_KEYWORDS),
-        "has_color": any(kw in text for kw in COLOR_KEYWORDS),
-        "has_counting": any(kw in text for kw in COUNTING_KEYWORDS),
-        "length": len(caption.split()),
-    }
+    f = _caption_features(caption)
+    return {"has_spatial": f[0], "has_color": f[1], "has_counting": f[2], "length": f[3]}
 
 
 def get_category_from_caption(caption: str) -> Optional[str]:
     """main.py:249-256: first supercategory (table order) with a keyword contained in the caption."""
-    text = caption.lower()
-    for name, keywords in COCO_SUPERCATEGORIES.items():
-        if any(kw in text for kw in keywords):
-            return name
-    return None
+    return _caption_features(caption)[4]
 
 
 def _pct(hits: int, total: int) -> float:
@@ -71,11 +84,11 @@ def aggregate_failure_from_hits(captions: Sequence[str], hits: np.ndarray, drawn
     total = int(drawn.sum())
     if total == 0:
         return {}
-    feats = [analyze_query_complexity(c) for c in captions]
-    cats = [get_category_from_caption(c) for c in captions]
+    raw = [_caption_features(c) for c in captions]
+    cats = [r[4] for r in raw]
     analysis: Dict[str, Any] = {"overall_accuracy": _pct(int(hits.sum()), total)}
-    for f in FEATURES:
-        mask = np.array([bool(x[f]) for x in feats], dtype=bool)
+    for fi, f in enumerate(FEATURES):
+        mask = np.fromiter((r[fi] for r in raw), dtype=bool, count=len(raw))
         if drawn[mask].sum() > 0:
             analysis[f"accuracy_{f}"] = _pct(int(hits[mask].sum()), int(drawn[mask].sum()))
         if drawn[~mask].sum() > 0:
@@ -92,7 +105,7 @@ def aggregate_failure_from_hits(captions: Sequence[str], hits: np.ndarray, drawn
             by_cat_h[c] = by_cat_h.get(c, 0) + int(hits[q])
             by_cat_n[c] += int(drawn[q])
     analysis["accuracy_by_category"] = {c: _pct(h, by_cat_n[c]) for c, h in by_cat_h.items()}
-    lengths = np.array([x["length"] for x in feats], dtype=np.int64)
+    lengths = np.fromiter((r[3] for r in raw), dtype=np.int64, count=len(raw))
     for lo, hi in LENGTH_BINS:
         mask = (lengths >= lo) & (lengths <= hi)
         if drawn[mask].sum() > 0:

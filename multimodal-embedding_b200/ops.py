@@ -53,6 +53,8 @@ class ProtocolRanks:
     col2unit: Optional[torch.Tensor] = None
     q_unit: Optional[torch.Tensor] = None
     scores: Optional[torch.Tensor] = None
+    top_s: Optional[torch.Tensor] = None      # [nq, k] fp32 top-k scores (KT), higher first, ties by lower column
+    top_i: Optional[torch.Tensor] = None      # [nq, k] int32 global column ids, -1 = padding
 
     @property
     def nq(self) -> int:
@@ -163,6 +165,56 @@ def rank_from_scores(scores: torch.Tensor, gt_off: torch.Tensor, gt_idx: torch.T
         _lib.check(h.mmx_rank_from_scores(scores.data_ptr(), nq, ng, ld, gt_off.data_ptr(), gt_idx.data_ptr(), g_base,
                                           MODE_COUNT, thr.data_ptr(), cnt.data_ptr(), _ptr(bits), wpr, _stream()))
     return ProtocolRanks(thr=thr, cnt_above=cnt, bits=bits, n_cols=ng)
+
+
+def topk_from_scores(scores: torch.Tensor, k: int = 10, g_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """KT. fp32 CUDA score matrix [nq, ng] -> (top_s fp32 [nq, k], top_i int32 [nq, k] global column ids):
+    ``torch.topk(scores[i], k)`` of main.py:333 for every row, ties ordered by column."""
+    _need_cuda(scores)
+    if scores.dtype != torch.float32:
+        raise TypeError("topk_from_scores takes fp32 scores")
+    if scores.dim() != 2 or (scores.shape[1] > 1 and scores.stride(1) != 1):
+        scores = scores.contiguous()
+    nq, ng = scores.shape
+    ld = scores.stride(0) if nq > 1 else max(ng, 1)
+    top_s = torch.empty((nq, k), dtype=torch.float32, device=scores.device)
+    top_i = torch.empty((nq, k), dtype=torch.int32, device=scores.device)
+    _lib.check(_lib.lib().mmx_topk_from_scores(scores.data_ptr(), nq, ng, ld, g_base, k, top_s.data_ptr(),
+                                               top_i.data_ptr(), _stream()))
+    return top_s, top_i
+
+
+def dense_topk(Q: torch.Tensor, G: torch.Tensor, k: int = 10, g_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """K1 top-k without the score matrix. Q [nq,d], G [ng,d] bf16 CUDA -> (top_s [nq,k], top_i [nq,k])."""
+    _need_cuda(Q, G)
+    if Q.dtype != torch.bfloat16 or G.dtype != torch.bfloat16:
+        raise TypeError("dense top-k kernel takes bf16 embeddings")
+    Q, G = Q.contiguous(), G.contiguous()
+    nq, d = Q.shape
+    ng = G.shape[0]
+    h = _lib.lib()
+    need = ctypes.c_size_t()
+    _lib.check(h.mmx_dense_topk_workspace_bytes(nq, ng, ctypes.byref(need)))
+    ws = torch.empty(need.value, dtype=torch.uint8, device=Q.device)
+    top_s = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+    top_i = torch.empty((nq, k), dtype=torch.int32, device=Q.device)
+    _lib.check(h.mmx_dense_topk(Q.data_ptr(), nq, G.data_ptr(), ng, d, g_base, k, top_s.data_ptr(), top_i.data_ptr(),
+                                ws.data_ptr(), need.value, _stream()))
+    return top_s, top_i
+
+
+def merge_topk(gathered_s: torch.Tensor, gathered_i: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-shard lists concatenated along columns ([nq, n_shards * k], global ids) -> global top-k."""
+    _need_cuda(gathered_s, gathered_i)
+    gathered_s, gathered_i = gathered_s.contiguous(), gathered_i.contiguous()
+    nq, width = gathered_s.shape
+    if width % k or gathered_i.shape != gathered_s.shape:
+        raise ValueError("gathered lists must be [nq, n_shards * k]")
+    top_s = torch.empty((nq, k), dtype=torch.float32, device=gathered_s.device)
+    top_i = torch.empty((nq, k), dtype=torch.int32, device=gathered_s.device)
+    _lib.check(_lib.lib().mmx_merge_topk(gathered_s.data_ptr(), gathered_i.data_ptr(), width // k, nq, k,
+                                         top_s.data_ptr(), top_i.data_ptr(), _stream()))
+    return top_s, top_i
 
 
 def bincount(sample_idx: torch.Tensor, n_units: int) -> torch.Tensor:

@@ -3,6 +3,8 @@ gallery columns split into contiguous shards, exactly two tiny collectives per s
 
   1. all-reduce(MAX) of the per-query GT thresholds (the GT column of a query lives on one shard only);
   2. all-reduce(SUM) of the strict-greater counts + all-gather of each shard's bitmask columns.
+When the retrieved items themselves are wanted, ONE all-gather of a fixed-size record per query — the shard's top-k
+scores and global column ids, 8k bytes — followed by a local merge (mmx_merge_topk) gives the global top-k.
 
 Counts and bit columns are additive / concatenable over gallery shards, so the merged structures are bit-identical
 to an unsharded pass (tests/test_gpu_parity.py::test_dense_arbitrary_gt_and_sharded_gallery checks the arithmetic,
@@ -53,3 +55,22 @@ def merge_ranks(local: ProtocolRanks, bounds: List[Tuple[int, int]], group=None)
         bits = torch.cat([p[:, : (e - b + 31) // 32] for p, (b, e) in zip(parts, bounds)], dim=1).contiguous()
     return ProtocolRanks(thr=local.thr, cnt_above=cnt, bits=bits, n_cols=bounds[-1][1], col2unit=local.col2unit,
                          q_unit=local.q_unit)
+
+
+def merge_topk(top_s: torch.Tensor, top_i: torch.Tensor, group=None, merge_fn=None):
+    """Global top-k from per-shard top-k lists with a single all-gather: every rank contributes one int32 record
+    [nq, 2k] (score bit patterns + global column ids), then merges the world's records locally.
+    `merge_fn(gathered_s, gathered_i, k)` defaults to the CUDA merge (ops.merge_topk); the gloo tests pass a CPU one."""
+    k = top_s.shape[1]
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return top_s, top_i
+    world = dist.get_world_size(group)
+    rec = torch.cat([top_s.contiguous().view(torch.int32), top_i], dim=1).contiguous()
+    parts = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(parts, rec, group=group)
+    gs = torch.cat([p[:, :k] for p in parts], dim=1).contiguous().view(torch.float32)
+    gi = torch.cat([p[:, k:] for p in parts], dim=1).contiguous()
+    if merge_fn is None:
+        from . import ops
+        merge_fn = ops.merge_topk
+    return merge_fn(gs, gi, k)

@@ -17,7 +17,7 @@ from .scoring import (  # noqa: F401
     dense_scores, maxsim_scores, maxsim_pad_flags, flatten_multivector,
 )
 from .metrics import (  # noqa: F401
-    compute_metrics_detailed, compute_metrics, above_gt_counts, recall_from_counts, METRIC_KEYS,
+    compute_metrics_detailed, compute_metrics, above_gt_counts, recall_from_counts, topk_lists, METRIC_KEYS,
 )
 from .stats import (  # noqa: F401
     pairwise_sum, np_mean, np_std, percentile_linear, bootstrap_confidence_interval, permutation_test,
@@ -26,3 +26,4 @@ from .stats import (  # noqa: F401
 from .bootstrap import (  # noqa: F401
     bootstrap_rescore_reference, bootstrap_identity, aggregate_row, CSV_COLUMNS,
 )
+from .legacy import compute_bidirectional_metrics, winoground_counts  # noqa: F401

@@ -153,3 +153,18 @@ def recall_from_counts(cnt, n: Optional[int] = None) -> Dict[int, float]:
     cnt = np.asarray(cnt)
     n = len(cnt) if n is None else n
     return {k: 100.0 * int((cnt < k).sum()) / n for k in KS}
+
+
+def topk_lists(scores: torch.Tensor, k: int = 10):
+    """`torch.topk(scores[i], k)` of main.py:333,362,372 for every row, with the tie order the CUDA path fixes
+    (higher score first, equal scores by lower column): a stable descending sort. Rows shorter than k are padded with
+    (-inf, -1). Returns (values fp32 [n, k], indices int64 [n, k])."""
+    s = scores.float()
+    n, g = s.shape
+    vals, idx = torch.sort(s, dim=1, descending=True, stable=True)
+    kk = min(k, g)
+    top_v = torch.full((n, k), float("-inf"))
+    top_i = torch.full((n, k), -1, dtype=torch.int64)
+    top_v[:, :kk] = vals[:, :kk]
+    top_i[:, :kk] = idx[:, :kk]
+    return top_v, top_i
