@@ -13,7 +13,7 @@ def run(qs, ds, d_zero=None, check=True, iters=0):
     nq, nd = len(qs), len(ds)
     scores = torch.full((nq, nd), float("nan"), device=dev)
     need = ctypes.c_size_t()
-    L.check(lib.mmx_maxsim_workspace_bytes(Q.shape[0], nd, ctypes.byref(need)))
+    L.check(lib.mmx_maxsim_workspace_bytes(Q.shape[0], nd, D.shape[0], ctypes.byref(need)))
     ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
     qo, do = q_off.to(dev), d_off.to(dev)
     dz = d_zero.to(dev) if d_zero is not None else None

@@ -6,7 +6,7 @@ dev = torch.device("cuda:0")
 Q, D, q2d = synth_maxsim(dev, NQ, ND, LQ, LD)
 q_off = torch.arange(0, NQ*LQ+1, LQ, dtype=torch.int32, device=dev); d_off = torch.arange(0, ND*LD+1, LD, dtype=torch.int32, device=dev)
 S = torch.empty(NQ, ND, device=dev)
-need = ctypes.c_size_t(); lib.mmx_maxsim_workspace_bytes(ctypes.c_int64(Q.shape[0]), ctypes.c_int64(ND), ctypes.byref(need))
+need = ctypes.c_size_t(); lib.mmx_maxsim_workspace_bytes(ctypes.c_int64(Q.shape[0]), ctypes.c_int64(ND), ctypes.c_int64(D.shape[0]), ctypes.byref(need))
 ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
 def call():
     rc = lib.mmx_maxsim_scores(ctypes.c_void_p(Q.data_ptr()), ctypes.c_void_p(q_off.data_ptr()), ctypes.c_int64(NQ), ctypes.c_int64(Q.shape[0]), ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(d_off.data_ptr()), ctypes.c_int64(ND), ctypes.c_int64(D.shape[0]), 128, None, ctypes.c_void_p(S.data_ptr()), ctypes.c_int64(ND), ctypes.c_void_p(ws.data_ptr()), ctypes.c_size_t(need.value), None)

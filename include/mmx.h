@@ -44,9 +44,12 @@ int mmx_device_check(void);
  * zero row inside the reference's 10-document chunk (the padded zero takes part in the max).
  * The role-swapped I2T orientation is the same call with images passed as q_* and captions as d_*.
  * Arithmetic: bf16 x bf16 products accumulated in fp32 on tcgen05, max and token sum in fp32.
- * workspace: mmx_maxsim_workspace_bytes(n_qtok, nd).
+ * Documents shorter than 256 rows on average (the role-swapped orientation: captions as documents) take a variant
+ * that first re-lays the documents out with lengths rounded up to a multiple of 4 rows (>= 16) by repeating a row of
+ * the same document, which cannot change a maximum; the scores are the same expression.
+ * workspace: mmx_maxsim_workspace_bytes(n_qtok, nd, n_dtok).
  */
-int mmx_maxsim_workspace_bytes(int64_t n_qtok, int64_t nd, size_t* bytes);
+int mmx_maxsim_workspace_bytes(int64_t n_qtok, int64_t nd, int64_t n_dtok, size_t* bytes);
 int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_t nq, int64_t n_qtok, const void* d_tok,
                       const int32_t* d_off, int64_t nd, int64_t n_dtok, int dim, const uint8_t* d_zero,
                       float* scores, int64_t ld_scores, void* workspace, size_t workspace_bytes,

@@ -63,7 +63,7 @@ _SIGNATURES = {
     "mmx_last_error": (_c.c_char_p, []),
     "mmx_abi_version": (_c.c_int, []),
     "mmx_device_check": (_c.c_int, []),
-    "mmx_maxsim_workspace_bytes": (_c.c_int, [_c.c_int64, _c.c_int64, _c.POINTER(_c.c_size_t)]),
+    "mmx_maxsim_workspace_bytes": (_c.c_int, [_c.c_int64, _c.c_int64, _c.c_int64, _c.POINTER(_c.c_size_t)]),
     "mmx_maxsim_scores": (_c.c_int, [
         _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64,      # q_tok, q_off, nq, n_qtok
         _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64,      # d_tok, d_off, nd, n_dtok

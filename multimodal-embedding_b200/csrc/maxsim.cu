@@ -30,6 +30,16 @@
 // one float per (query, doc) — the drain warps never wait for that work. A query whose tokens straddle two row
 // tiles gets its tail part in `carry[tile, doc]`, folded in by maxsim_fixup_kernel in tile order — no floating-point
 // atomics anywhere.
+//
+// SHORT-document variant (template flag; the role-swapped I2T orientation of v28 :375-386 / main.py:622, where the
+// "documents" are captions of ~20 tokens and a document closes every ~20 accumulator columns): the documents are
+// first re-laid out with every length rounded up to a multiple of 4 rows, at least 16, by repeating a row of the same
+// document (a duplicate cannot change a maximum; an empty document becomes zero rows, whose maxima are 0 like the
+// reference's zero padding). Boundaries then fall on 4-column groups and are the same for every thread, so the drain
+// is branch-uniform: 8 group maxima per 32-column chunk, a running maximum, and one shared-memory store per closed
+// document into M[accumulator][slot][row] (at most 16 documents end inside one 256-column tile). Warps 4-7 drain
+// accumulator 0 and warps 8-11 accumulator 1 (all 256 columns each: no half merging), and the reducer sums the rows
+// of a whole tile's documents at once, one lane per document, instead of one latency-bound shuffle tree per document.
 #include <cfloat>
 #include <climits>
 
@@ -53,6 +63,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int HALF_COLS = BN / 2;                // columns of one accumulator drained by one warp
 constexpr int NSLOT = 4;                         // parked-document slots per accumulator
 constexpr long long L2_CHUNK_BYTES = 24ll << 20; // document chunk kept hot in the 126 MB L2
+constexpr int SHORT_ALIGN = 4;                   // SHORT variant: padded document lengths are multiples of this ...
+constexpr int SHORT_MIN = 16;                    // ... and at least this, so at most BN / SHORT_MIN documents end per tile
+constexpr int MSLOTS = BN / SHORT_MIN;           // 16
+constexpr long long SHORT_AVG_ROWS = 256;        // documents shorter than this on average take the SHORT variant
 
 struct Params {
     const int32_t* q_off;   // [nq+1] token offsets
@@ -62,6 +76,7 @@ struct Params {
     float* scores;          // [nq, ld_scores]
     long long ld_scores;
     float* carry;           // [n_mtiles, nd] partial sums of queries continued from the previous row tile
+    const uint32_t* ends;   // SHORT: bit g = a document ends after 4-row group g of the padded document matrix
     int nq, nd, n_qtok, n_dtok;
     int n_mtiles, n_mpairs, n_chunks, docs_per_chunk;
 };
@@ -69,18 +84,22 @@ struct Params {
 struct __align__(1024) Smem {
     uint8_t a[2][A_TILE_BYTES];
     uint8_t b[NSTAGE][B_STAGE_BYTES];
-    float stage[2][NSLOT][2][BM];  // [accumulator][slot][column half][row] row maxima of a closed document
+    union {
+        float stage[2][NSLOT][2][BM];  // [accumulator][slot][column half][row] row maxima of a closed document
+        float M[2][MSLOTS][BM];        // SHORT: [accumulator][document slot][row ^ slot] row maxima of a tile's documents
+    };
     int seg_start[2][BM + 1];      // reducer-private: query segments of the two row tiles
     int seg_q[2][BM];
     uint64_t a_full, a_free;
     uint64_t b_full[NSTAGE], b_empty[NSTAGE];
     uint64_t t_full[2], t_empty[2];
     uint64_t st_full[2][NSLOT], st_empty[2][NSLOT];
+    uint64_t batch_full[2], batch_empty[2];  // SHORT: M[a] written by the 4 drain warps / consumed by the reducer
     uint32_t tmem_base;
 };
 
 struct ItemGeom {
-    int mp, d0, d1, p0, ntiles;
+    int mp, d0, d1, p0, p1, ntiles;
 };
 
 __device__ __forceinline__ ItemGeom item_geom(const Params& p, int item) {
@@ -90,8 +109,8 @@ __device__ __forceinline__ ItemGeom item_geom(const Params& p, int item) {
     g.d0 = ch * p.docs_per_chunk;
     g.d1 = min(p.nd, g.d0 + p.docs_per_chunk);
     g.p0 = __ldg(p.d_off + g.d0);
-    const int p1 = __ldg(p.d_off + g.d1);
-    g.ntiles = (p1 - g.p0 + BN - 1) / BN;
+    g.p1 = __ldg(p.d_off + g.d1);
+    g.ntiles = (g.p1 - g.p0 + BN - 1) / BN;
     return g;
 }
 
@@ -316,6 +335,42 @@ __device__ __forceinline__ void reduce_doc(Smem& s, const Params& p, Reducer& r,
     }
 }
 
+// ---------------------------------------------------------------------------------------------- SHORT variant
+// Which 4-column groups of the tile starting at (padded) row pt end a document: 64 bits, uniform over the CTA.
+__device__ __forceinline__ uint64_t tile_ends(const Params& p, int pt, int p1) {
+    const int g0 = pt >> 2;
+    const int w = g0 >> 5, sh = g0 & 31;
+    const uint32_t a = __ldg(p.ends + w), b = __ldg(p.ends + w + 1), c = __ldg(p.ends + w + 2);
+    uint64_t m = (uint64_t)__funnelshift_r(a, b, sh) | ((uint64_t)__funnelshift_r(b, c, sh) << 32);
+    const int valid = (p1 - pt) >> 2;  // groups of this tile that still belong to the chunk
+    if (valid < 64) m &= (valid <= 0) ? 0ull : ((1ull << valid) - 1ull);
+    return m;
+}
+
+// 32 accumulator columns = 8 groups of 4; e8 = which groups end a document (same for every thread of the CTA).
+__device__ __forceinline__ void fold_short(const uint32_t (&v)[32], float& m, uint32_t e8, float* Macc, int row,
+                                           int& slot) {
+    float g4[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        g4[k] = fmaxf(max3(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2])),
+                      __uint_as_float(v[4 * k + 3]));
+    if (e8 == 0u) {
+        m = max3(max3(m, g4[0], g4[1]), max3(g4[2], g4[3], g4[4]), max3(g4[5], g4[6], g4[7]));
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        m = fmaxf(m, g4[k]);
+        if (e8 & (1u << k)) {
+            Macc[slot * BM + (row ^ slot)] = m;
+            m = -INFINITY;
+            ++slot;
+        }
+    }
+}
+
+template <bool SHORT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
               const __grid_constant__ Params p) {
@@ -337,7 +392,9 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.t_full[i], 1);
-            mbar_init(&s.t_empty[i], 8);  // one arrival per drain warp
+            mbar_init(&s.t_empty[i], SHORT ? 4 : 8);  // one arrival per drain warp of this accumulator
+            mbar_init(&s.batch_full[i], 4);
+            mbar_init(&s.batch_empty[i], 1);
             for (int j = 0; j < NSLOT; ++j) {
                 mbar_init(&s.st_full[i][j], 8);
                 mbar_init(&s.st_empty[i][j], 1);
@@ -410,6 +467,71 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 umma_commit(&s.a_free);
             }
         }
+    } else if (warp == 3 && SHORT) {
+        // ------------------------------------------------------------------ SHORT reducer: one lane per document of
+        // the tile; every lane walks the same rows (uniform segment boundaries), M is read conflict-free (row ^ slot)
+        uint32_t use[2] = {0, 0};
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const ItemGeom g = item_geom(p, item);
+            const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
+            int nseg[2], cont[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int r0 = (g.mp * 2 + a) * BM;
+                cont[a] = (r0 > 0) && (r0 < p.n_qtok) && (__ldg(p.tok2q + r0 - 1) == __ldg(p.tok2q + r0));
+                nseg[a] = (a < nm) ? build_segments(s, p, a, g.mp * 2 + a, lane) : 0;
+            }
+            int first = g.d0;
+            for (int t = 0; t < g.ntiles; ++t) {
+                const uint64_t ends = tile_ends(p, g.p0 + t * BN, g.p1);
+                const int n = __popcll(ends);
+                const bool act = lane < n;
+                const int doc = first + lane;
+                const bool zero = act && p.d_zero != nullptr && p.d_zero[doc] != 0;
+                for (int a = 0; a < nm; ++a) {
+                    mbar_wait(&s.batch_full[a], use[a] & 1);
+                    if (act) {
+                        const float* M = &s.M[a][lane & (MSLOTS - 1)][0];
+                        const long long mt = g.mp * 2 + a;
+#pragma unroll 1
+                        for (int si = 0; si < nseg[a]; ++si) {
+                            const int ra = s.seg_start[a][si], rb = s.seg_start[a][si + 1];
+                            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                            int r = ra;
+                            if (zero) {
+                                for (; r + 4 <= rb; r += 4) {
+                                    a0 += fmaxf(M[(r) ^ lane], 0.0f);
+                                    a1 += fmaxf(M[(r + 1) ^ lane], 0.0f);
+                                    a2 += fmaxf(M[(r + 2) ^ lane], 0.0f);
+                                    a3 += fmaxf(M[(r + 3) ^ lane], 0.0f);
+                                }
+                                for (; r < rb; ++r) a0 += fmaxf(M[r ^ lane], 0.0f);
+                            } else {
+                                for (; r + 4 <= rb; r += 4) {
+                                    a0 += M[(r) ^ lane];
+                                    a1 += M[(r + 1) ^ lane];
+                                    a2 += M[(r + 2) ^ lane];
+                                    a3 += M[(r + 3) ^ lane];
+                                }
+                                for (; r < rb; ++r) a0 += M[r ^ lane];
+                            }
+                            const float sum = (a0 + a1) + (a2 + a3);
+                            const int q = s.seg_q[a][si];
+                            if (q >= 0) {
+                                if (si == 0 && cont[a])
+                                    p.carry[mt * p.nd + doc] = sum;
+                                else
+                                    p.scores[(long long)q * p.ld_scores + doc] = sum;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s.batch_empty[a]);
+                    use[a]++;
+                }
+                first += n;
+            }
+        }
     } else if (warp == 3) {
         // ------------------------------------------------------------------ reducer: replays the drain warps'
         // sequence of closed documents (it depends on d_off only) and finishes each one
@@ -443,6 +565,57 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                     reduce_doc(s, p, r[a], a, cur[a], lane);
                     cur[a]++;
                 }
+        }
+    } else if (warp >= 4 && SHORT) {
+        // ------------------------------------------------------------------ SHORT drain: warps 4-7 own accumulator 0,
+        // warps 8-11 accumulator 1 (all 256 columns); document boundaries are uniform 4-column group ends
+        const int a = (warp - 4) >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t ta = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + a * BN;
+        float* Macc = &s.M[a][0][0];
+        uint32_t use = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const ItemGeom g = item_geom(p, item);
+            const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
+            if (a >= nm) continue;
+            float m = -INFINITY;
+#pragma unroll 1
+            for (int t = 0; t < g.ntiles; ++t, ++use) {
+                const uint64_t ends = tile_ends(p, g.p0 + t * BN, g.p1);
+                const uint32_t elo = (uint32_t)ends, ehi = (uint32_t)(ends >> 32);
+                mbar_wait(&s.t_full[a], use & 1);
+                tc_fence_after();
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32(ta, va);
+                mbar_wait(&s.batch_empty[a], (use & 1) ^ 1);  // the reducer is done with this accumulator's last tile
+                int slot = 0;
+                tmem_ld_wait();
+                tmem_ld_32x32(ta + 32, vb);
+                fold_short(va, m, elo & 0xffu, Macc, row, slot);
+                tmem_ld_wait();
+                tmem_ld_32x32(ta + 64, va);
+                fold_short(vb, m, (elo >> 8) & 0xffu, Macc, row, slot);
+                tmem_ld_wait();
+                tmem_ld_32x32(ta + 96, vb);
+                fold_short(va, m, (elo >> 16) & 0xffu, Macc, row, slot);
+                tmem_ld_wait();
+                tmem_ld_32x32(ta + 128, va);
+                fold_short(vb, m, elo >> 24, Macc, row, slot);
+                tmem_ld_wait();
+                tmem_ld_32x32(ta + 160, vb);
+                fold_short(va, m, ehi & 0xffu, Macc, row, slot);
+                tmem_ld_wait();
+                tmem_ld_32x32(ta + 192, va);
+                fold_short(vb, m, (ehi >> 8) & 0xffu, Macc, row, slot);
+                tmem_ld_wait();
+                tmem_ld_32x32(ta + 224, vb);
+                fold_short(va, m, (ehi >> 16) & 0xffu, Macc, row, slot);
+                tmem_ld_wait();
+                release_accumulator(s, a, lane);
+                fold_short(vb, m, ehi >> 24, Macc, row, slot);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.batch_full[a]);
+            }
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ drain warps (8 warps, 256 threads)
@@ -514,19 +687,105 @@ __global__ void maxsim_fixup_kernel(const int32_t* __restrict__ tok2q, const int
     scores[(long long)q * ld + d] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------- SHORT prep
+__host__ __device__ __forceinline__ int short_padded_len(int L) {
+    const int r = (L + SHORT_ALIGN - 1) & ~(SHORT_ALIGN - 1);
+    return r < SHORT_MIN ? SHORT_MIN : r;
+}
+
+// pd_off[d] = exclusive prefix sum of the padded document lengths (one block; nd / 1024 sequential rounds)
+__global__ void __launch_bounds__(1024)
+short_offsets_kernel(const int32_t* __restrict__ d_off, int nd, int32_t* __restrict__ pd_off) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nd; base += 1024) {
+        const int d = base + t;
+        const int len = d < nd ? short_padded_len(d_off[d + 1] - d_off[d]) : 0;
+        int incl = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_tot[lane] = w;  // inclusive totals of the warps
+        }
+        __syncthreads();
+        const int before = carry_s + (warp > 0 ? warp_tot[warp - 1] : 0) + incl - len;
+        if (d < nd) pd_off[d] = before;
+        __syncthreads();
+        if (t == 1023) carry_s = before + len;
+        __syncthreads();
+    }
+    if (t == 0) pd_off[nd] = carry_s;
+}
+
+// one warp per document: copy its rows into the padded matrix, fill the tail with copies of its first row (zeros
+// for an empty document), and mark the group that ends it
+__global__ void __launch_bounds__(256)
+short_pad_docs_kernel(const uint2* __restrict__ d_tok, const int32_t* __restrict__ d_off,
+                      const int32_t* __restrict__ pd_off, int nd, uint2* __restrict__ out, uint32_t* __restrict__ ends) {
+    const int lane = threadIdx.x & 31;
+    const int d = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (d >= nd) return;
+    const long long src = d_off[d], L = d_off[d + 1] - src;
+    const long long dst = pd_off[d], Lp = pd_off[d + 1] - dst;
+    for (long long r = 0; r < Lp; ++r) {
+        uint2 v = make_uint2(0u, 0u);
+        if (L > 0) v = d_tok[(src + (r < L ? r : 0)) * 32 + lane];  // a row is 128 bf16 = 32 x 8 bytes
+        out[(dst + r) * 32 + lane] = v;
+    }
+    if (lane == 0) {
+        const long long g = ((dst + Lp) >> 2) - 1;
+        atomicOr(ends + (g >> 5), 1u << (g & 31));
+    }
+}
+
 }  // namespace maxsim
 }  // namespace mmx
 
 using namespace mmx;
 using namespace mmx::maxsim;
 
-extern "C" int mmx_maxsim_workspace_bytes(int64_t n_qtok, int64_t nd, size_t* bytes) {
-    MMX_REQUIRE(bytes != nullptr, "bytes == NULL");
+namespace {
+struct WsPlan {
+    bool shortdocs;
+    long long pad_rows;  // upper bound of the padded document matrix
+    size_t off_tok2q, off_carry, off_pdoff, off_ends, off_pad, total;
+};
+WsPlan plan_ws(int64_t n_qtok, int64_t nd, int64_t n_dtok) {
+    WsPlan w{};
+    auto up = [](size_t x) { return (x + 1023) & ~size_t(1023); };
     const int64_t n_mtiles = (n_qtok + BM - 1) / BM;
-    size_t b = 0;
-    b += ((size_t)n_qtok * 4 + 255) & ~size_t(255);
-    b += (size_t)n_mtiles * (size_t)nd * 4;
-    *bytes = b + 256;
+    w.shortdocs = nd > 0 && n_dtok < SHORT_AVG_ROWS * nd;
+    size_t o = 1024;
+    w.off_tok2q = o; o += up((size_t)n_qtok * 4);
+    w.off_carry = o; o += up((size_t)n_mtiles * (size_t)nd * 4);
+    if (w.shortdocs) {
+        w.pad_rows = n_dtok + (long long)SHORT_MIN * nd + BN;
+        w.off_pdoff = o; o += up((size_t)(nd + 1) * 4);
+        w.off_ends = o;  o += up((size_t)(w.pad_rows / 4 / 32 + 4) * 4);
+        w.off_pad = o;   o += up((size_t)w.pad_rows * DIM * 2);
+    }
+    w.total = o;
+    return w;
+}
+}  // namespace
+
+extern "C" int mmx_maxsim_workspace_bytes(int64_t n_qtok, int64_t nd, int64_t n_dtok, size_t* bytes) {
+    MMX_REQUIRE(bytes != nullptr && n_qtok >= 0 && nd >= 0 && n_dtok >= 0, "bad argument");
+    *bytes = plan_ws(n_qtok, nd, n_dtok).total;
     return 0;
 }
 
@@ -545,19 +804,36 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
     MMX_CHECK_CUDA(cudaMemset2DAsync(scores, (size_t)ld_scores * sizeof(float), 0, (size_t)nd * sizeof(float),
                                      (size_t)nq, stream));
     if (n_qtok == 0) return 0;
-    size_t need = 0;
-    mmx_maxsim_workspace_bytes(n_qtok, nd, &need);
-    MMX_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small: need %zu bytes, got %zu", need,
-                workspace_bytes);
+    const WsPlan wp = plan_ws(n_qtok, nd, n_dtok);
+    MMX_REQUIRE(workspace != nullptr && workspace_bytes >= wp.total, "workspace too small: need %zu bytes, got %zu",
+                wp.total, workspace_bytes);
+    MMX_REQUIRE(!wp.shortdocs || wp.pad_rows < (1ll << 31) - 512, "padded document matrix exceeds int32 offsets");
 
     Params p;
     p.q_off = q_off;
     p.d_off = d_off;
-    uintptr_t ws = (reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255);
-    int32_t* tok2q = reinterpret_cast<int32_t*>(ws);
-    ws += ((size_t)n_qtok * 4 + 255) & ~size_t(255);
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 1023) & ~uintptr_t(1023));
+    int32_t* tok2q = reinterpret_cast<int32_t*>(ws + wp.off_tok2q - 1024);
     p.tok2q = tok2q;
-    p.carry = reinterpret_cast<float*>(ws);
+    p.carry = reinterpret_cast<float*>(ws + wp.off_carry - 1024);
+    p.ends = nullptr;
+    const void* d_mat = d_tok;
+    long long d_rows = n_dtok;
+    if (wp.shortdocs) {
+        // re-lay the documents out with lengths rounded up to a multiple of 4 (>= 16) rows
+        int32_t* pd_off = reinterpret_cast<int32_t*>(ws + wp.off_pdoff - 1024);
+        uint32_t* ends = reinterpret_cast<uint32_t*>(ws + wp.off_ends - 1024);
+        void* pad = ws + wp.off_pad - 1024;
+        MMX_CHECK_CUDA(cudaMemsetAsync(ends, 0, (size_t)(wp.pad_rows / 4 / 32 + 4) * 4, stream));
+        short_offsets_kernel<<<1, 1024, 0, stream>>>(d_off, (int)nd, pd_off);
+        short_pad_docs_kernel<<<(unsigned)((nd + 7) / 8), 256, 0, stream>>>(
+            reinterpret_cast<const uint2*>(d_tok), d_off, pd_off, (int)nd, reinterpret_cast<uint2*>(pad), ends);
+        MMX_CHECK_CUDA(cudaGetLastError());
+        p.d_off = pd_off;
+        p.ends = ends;
+        d_mat = pad;
+        d_rows = wp.pad_rows;
+    }
     p.d_zero = d_zero;
     p.scores = scores;
     p.ld_scores = ld_scores;
@@ -583,7 +859,7 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
 
     CUtensorMap tq, td;
     if (make_tmap_bf16_sw128(&tq, q_tok, (uint64_t)n_qtok, DIM, DIM, BM) != 0) return -4;
-    if (make_tmap_bf16_sw128(&td, d_tok, (uint64_t)(n_dtok > 0 ? n_dtok : 1), DIM, DIM, BN) != 0) return -4;
+    if (make_tmap_bf16_sw128(&td, d_mat, (uint64_t)(d_rows > 0 ? d_rows : 1), DIM, DIM, BN) != 0) return -4;
 
     tok2q_kernel<<<(unsigned)((n_qtok + 255) / 256), 256, 0, stream>>>(q_off, (int)nq, (int)n_qtok, tok2q);
     MMX_CHECK_CUDA(cudaGetLastError());
@@ -591,12 +867,16 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
     const size_t smem_bytes = sizeof(Smem) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        MMX_CHECK_CUDA(cudaFuncSetAttribute(maxsim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(maxsim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(maxsim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_set = true;
     }
     const long long n_items = (long long)p.n_mpairs * p.n_chunks;
     const int grid = (int)(n_items < sms ? n_items : sms);
-    maxsim_kernel<<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, td, p);
+    if (wp.shortdocs)
+        maxsim_kernel<true><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, td, p);
+    else
+        maxsim_kernel<false><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, td, p);
     MMX_CHECK_CUDA(cudaGetLastError());
 
     if (p.n_mtiles > 1) {

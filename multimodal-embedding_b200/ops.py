@@ -81,7 +81,7 @@ def maxsim_scores(q_tok: torch.Tensor, q_off: torch.Tensor, d_tok: torch.Tensor,
         out = torch.empty((nq, nd), dtype=torch.float32, device=q_tok.device)
     need = ctypes.c_size_t()
     h = _lib.lib()
-    _lib.check(h.mmx_maxsim_workspace_bytes(q_tok.shape[0], nd, ctypes.byref(need)))
+    _lib.check(h.mmx_maxsim_workspace_bytes(q_tok.shape[0], nd, d_tok.shape[0], ctypes.byref(need)))
     ws = torch.empty(need.value, dtype=torch.uint8, device=q_tok.device)
     _lib.check(h.mmx_maxsim_scores(q_tok.data_ptr(), q_off.data_ptr(), nq, q_tok.shape[0], d_tok.data_ptr(),
                                    d_off.data_ptr(), nd, d_tok.shape[0], q_tok.shape[1] if q_tok.dim() == 2 else 0,
