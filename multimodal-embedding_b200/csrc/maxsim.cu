@@ -66,6 +66,7 @@ constexpr long long L2_CHUNK_BYTES = 24ll << 20; // document chunk kept hot in t
 constexpr int SHORT_ALIGN = 4;                   // SHORT variant: padded document lengths are multiples of this ...
 constexpr int SHORT_MIN = 16;                    // ... and at least this, so at most BN / SHORT_MIN documents end per tile
 constexpr int MSLOTS = BN / SHORT_MIN;           // 16
+constexpr int MSTRIDE = BM + 1;                  // row pitch of M in floats: slot * 129 + row is conflict-free both ways
 constexpr long long SHORT_AVG_ROWS = 256;        // documents shorter than this on average take the SHORT variant
 
 struct Params {
@@ -86,7 +87,7 @@ struct __align__(1024) Smem {
     uint8_t b[NSTAGE][B_STAGE_BYTES];
     union {
         float stage[2][NSLOT][2][BM];  // [accumulator][slot][column half][row] row maxima of a closed document
-        float M[2][MSLOTS][BM];        // SHORT: [accumulator][document slot][row ^ slot] row maxima of a tile's documents
+        float M[2][MSLOTS][MSTRIDE];   // SHORT: [accumulator][document slot][row] row maxima of a tile's documents
     };
     int seg_start[2][BM + 1];      // reducer-private: query segments of the two row tiles
     int seg_q[2][BM];
@@ -347,25 +348,128 @@ __device__ __forceinline__ uint64_t tile_ends(const Params& p, int pt, int p1) {
     return m;
 }
 
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // 32 accumulator columns = 8 groups of 4; e8 = which groups end a document (same for every thread of the CTA).
-__device__ __forceinline__ void fold_short(const uint32_t (&v)[32], float& m, uint32_t e8, float* Macc, int row,
-                                           int& slot) {
+// addr = shared-space byte address of M[accumulator][next free slot][row]; a closed document's maximum is stored
+// there and the address moves on one slot. Branch-free: one predicate per group drives the store, the reset of the
+// running maximum and the address step.
+__device__ __forceinline__ void fold_short(const uint32_t (&v)[32], float& m, uint32_t e8, uint32_t& addr) {
     float g4[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k)
         g4[k] = fmaxf(max3(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2])),
                       __uint_as_float(v[4 * k + 3]));
-    if (e8 == 0u) {
-        m = max3(max3(m, g4[0], g4[1]), max3(g4[2], g4[3], g4[4]), max3(g4[5], g4[6], g4[7]));
-        return;
-    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         m = fmaxf(m, g4[k]);
-        if (e8 & (1u << k)) {
-            Macc[slot * BM + (row ^ slot)] = m;
-            m = -INFINITY;
-            ++slot;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %2, 0;\n\t"
+            "@p st.shared.f32 [%0], %1;\n\t"
+            "@p mov.b32 %1, 0xff800000;\n\t"
+            "@p add.u32 %0, %0, %3;\n\t}"
+            : "+r"(addr), "+f"(m)
+            : "r"(e8 & (1u << k)), "n"(MSTRIDE * 4)
+            : "memory");
+    }
+}
+
+// SHORT reducer of accumulator a: per tile, two lanes per document (lane = slot + 16 * h; the halves take alternate
+// blocks of 16 rows, which keeps the reads of M[slot][row] free of bank conflicts); every lane walks the same
+// segment table and the partial sums are combined in a fixed order. Rows of a segment that fill whole 32-row pairs
+// are summed without any range test; only the ragged edges of a segment (one tile in eight holds a query boundary
+// when the queries are 1030-row images) take the predicated loop.
+__device__ __forceinline__ float red_edge(uint32_t M, int r_lo, int r_hi, int h, float floor_v) {
+    float acc = 0.0f;
+    for (int r = r_lo; r < r_hi; ++r)
+        if (((r >> 4) & 1) == h) acc += fmaxf(lds_f32(M + 4u * (uint32_t)r), floor_v);
+    return acc;
+}
+
+__device__ __forceinline__ void short_reducer(Smem& s, const Params& p, int a, int lane, int n_items) {
+    const int j = lane & (MSLOTS - 1), h = lane >> 4;
+    const bool flags = p.d_zero != nullptr;
+    uint32_t use = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ItemGeom g = item_geom(p, item);
+        const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
+        if (a >= nm) continue;
+        const long long mt = g.mp * 2 + a;
+        const int r0 = (int)mt * BM;
+        const bool cont = (r0 > 0) && (r0 < p.n_qtok) && (__ldg(p.tok2q + r0 - 1) == __ldg(p.tok2q + r0));
+        const int nseg = build_segments(s, p, a, (int)mt, lane);
+        int first = g.d0;
+        uint64_t ends_next = tile_ends(p, g.p0, g.p1);
+        uint8_t zflag_next = (flags && first + j < p.nd) ? __ldg(p.d_zero + first + j) : (uint8_t)0;
+        const uint32_t M = smem_u32(&s.M[a][j][0]);
+        for (int t = 0; t < g.ntiles; ++t, ++use) {
+            const uint64_t ends = ends_next;
+            const uint8_t zflag = zflag_next;
+            const int n = __popcll(ends);
+            // next tile's boundary words and padding flags travel from L2 while this tile is reduced
+            if (t + 1 < g.ntiles) {
+                ends_next = tile_ends(p, g.p0 + (t + 1) * BN, g.p1);
+                zflag_next = (flags && first + n + j < p.nd) ? __ldg(p.d_zero + first + n + j) : (uint8_t)0;
+            }
+            const bool act = j < n;
+            const int doc = first + j;
+            const float floor_v = (act && zflag) ? 0.0f : -INFINITY;  // max(x, -inf) = x: one code path for both
+            mbar_wait(&s.batch_full[a], use & 1);
+#pragma unroll 1
+            for (int si = 0; si < nseg; ++si) {
+                const int ra = s.seg_start[a][si], rb = s.seg_start[a][si + 1];
+                float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+                if (act) {
+                    const int f0 = (ra + 31) & ~31, f1 = rb & ~31;  // whole 32-row pairs are [f0, f1)
+                    if (f0 <= f1) {
+                        a0 = red_edge(M, ra, f0, h, floor_v);
+                        a1 = red_edge(M, f1, rb, h, floor_v);
+#pragma unroll 1
+                        for (int base = f0 + 16 * h; base < f1; base += 32) {
+                            const uint32_t mb = M + 4u * (uint32_t)base;
+                            if (flags) {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    a0 += fmaxf(lds_f32(mb + 4 * i), floor_v);
+                                    a1 += fmaxf(lds_f32(mb + 4 * i + 4), floor_v);
+                                    a2 += fmaxf(lds_f32(mb + 4 * i + 8), floor_v);
+                                    a3 += fmaxf(lds_f32(mb + 4 * i + 12), floor_v);
+                                }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; i += 4) {
+                                    a0 += lds_f32(mb + 4 * i);
+                                    a1 += lds_f32(mb + 4 * i + 4);
+                                    a2 += lds_f32(mb + 4 * i + 8);
+                                    a3 += lds_f32(mb + 4 * i + 12);
+                                }
+                            }
+                        }
+                    } else {
+                        a0 = red_edge(M, ra, rb, h, floor_v);  // the segment lies inside one 32-row pair
+                    }
+                }
+                float sum = (a0 + a1) + (a2 + a3);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                const int q = s.seg_q[a][si];
+                if (act && h == 0 && q >= 0) {
+                    if (si == 0 && cont)
+                        p.carry[mt * p.nd + doc] = sum;
+                    else
+                        p.scores[(long long)q * p.ld_scores + doc] = sum;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.batch_empty[a]);
+            first += n;
         }
     }
 }
@@ -467,71 +571,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 umma_commit(&s.a_free);
             }
         }
-    } else if (warp == 3 && SHORT) {
-        // ------------------------------------------------------------------ SHORT reducer: one lane per document of
-        // the tile; every lane walks the same rows (uniform segment boundaries), M is read conflict-free (row ^ slot)
-        uint32_t use[2] = {0, 0};
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-            const ItemGeom g = item_geom(p, item);
-            const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
-            int nseg[2], cont[2];
-#pragma unroll
-            for (int a = 0; a < 2; ++a) {
-                const int r0 = (g.mp * 2 + a) * BM;
-                cont[a] = (r0 > 0) && (r0 < p.n_qtok) && (__ldg(p.tok2q + r0 - 1) == __ldg(p.tok2q + r0));
-                nseg[a] = (a < nm) ? build_segments(s, p, a, g.mp * 2 + a, lane) : 0;
-            }
-            int first = g.d0;
-            for (int t = 0; t < g.ntiles; ++t) {
-                const uint64_t ends = tile_ends(p, g.p0 + t * BN, g.p1);
-                const int n = __popcll(ends);
-                const bool act = lane < n;
-                const int doc = first + lane;
-                const bool zero = act && p.d_zero != nullptr && p.d_zero[doc] != 0;
-                for (int a = 0; a < nm; ++a) {
-                    mbar_wait(&s.batch_full[a], use[a] & 1);
-                    if (act) {
-                        const float* M = &s.M[a][lane & (MSLOTS - 1)][0];
-                        const long long mt = g.mp * 2 + a;
-#pragma unroll 1
-                        for (int si = 0; si < nseg[a]; ++si) {
-                            const int ra = s.seg_start[a][si], rb = s.seg_start[a][si + 1];
-                            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-                            int r = ra;
-                            if (zero) {
-                                for (; r + 4 <= rb; r += 4) {
-                                    a0 += fmaxf(M[(r) ^ lane], 0.0f);
-                                    a1 += fmaxf(M[(r + 1) ^ lane], 0.0f);
-                                    a2 += fmaxf(M[(r + 2) ^ lane], 0.0f);
-                                    a3 += fmaxf(M[(r + 3) ^ lane], 0.0f);
-                                }
-                                for (; r < rb; ++r) a0 += fmaxf(M[r ^ lane], 0.0f);
-                            } else {
-                                for (; r + 4 <= rb; r += 4) {
-                                    a0 += M[(r) ^ lane];
-                                    a1 += M[(r + 1) ^ lane];
-                                    a2 += M[(r + 2) ^ lane];
-                                    a3 += M[(r + 3) ^ lane];
-                                }
-                                for (; r < rb; ++r) a0 += M[r ^ lane];
-                            }
-                            const float sum = (a0 + a1) + (a2 + a3);
-                            const int q = s.seg_q[a][si];
-                            if (q >= 0) {
-                                if (si == 0 && cont[a])
-                                    p.carry[mt * p.nd + doc] = sum;
-                                else
-                                    p.scores[(long long)q * p.ld_scores + doc] = sum;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s.batch_empty[a]);
-                    use[a]++;
-                }
-                first += n;
-            }
-        }
+    } else if ((warp == 2 || warp == 3) && SHORT) {
+        // ------------------------------------------------------------------ SHORT reducers: warp 2 finishes
+        // accumulator 0, warp 3 accumulator 1
+        short_reducer(s, p, warp - 2, lane, n_items);
     } else if (warp == 3) {
         // ------------------------------------------------------------------ reducer: replays the drain warps'
         // sequence of closed documents (it depends on d_off only) and finishes each one
@@ -572,47 +615,50 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const int a = (warp - 4) >> 2;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t ta = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + a * BN;
-        float* Macc = &s.M[a][0][0];
+        const uint32_t Mrow = smem_u32(&s.M[a][0][0]) + 4u * (uint32_t)row;
         uint32_t use = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ItemGeom g = item_geom(p, item);
             const int nm = (g.mp * 2 + 1 < p.n_mtiles) ? 2 : 1;
             if (a >= nm) continue;
             float m = -INFINITY;
+            uint64_t ends_next = tile_ends(p, g.p0, g.p1);
 #pragma unroll 1
             for (int t = 0; t < g.ntiles; ++t, ++use) {
-                const uint64_t ends = tile_ends(p, g.p0 + t * BN, g.p1);
+                const uint64_t ends = ends_next;
+                // the next tile's boundary words travel from L2 while this tile is drained
+                if (t + 1 < g.ntiles) ends_next = tile_ends(p, g.p0 + (t + 1) * BN, g.p1);
                 const uint32_t elo = (uint32_t)ends, ehi = (uint32_t)(ends >> 32);
                 mbar_wait(&s.t_full[a], use & 1);
                 tc_fence_after();
                 uint32_t va[32], vb[32];
                 tmem_ld_32x32(ta, va);
                 mbar_wait(&s.batch_empty[a], (use & 1) ^ 1);  // the reducer is done with this accumulator's last tile
-                int slot = 0;
+                uint32_t addr = Mrow;
                 tmem_ld_wait();
                 tmem_ld_32x32(ta + 32, vb);
-                fold_short(va, m, elo & 0xffu, Macc, row, slot);
+                fold_short(va, m, elo & 0xffu, addr);
                 tmem_ld_wait();
                 tmem_ld_32x32(ta + 64, va);
-                fold_short(vb, m, (elo >> 8) & 0xffu, Macc, row, slot);
+                fold_short(vb, m, (elo >> 8) & 0xffu, addr);
                 tmem_ld_wait();
                 tmem_ld_32x32(ta + 96, vb);
-                fold_short(va, m, (elo >> 16) & 0xffu, Macc, row, slot);
+                fold_short(va, m, (elo >> 16) & 0xffu, addr);
                 tmem_ld_wait();
                 tmem_ld_32x32(ta + 128, va);
-                fold_short(vb, m, elo >> 24, Macc, row, slot);
+                fold_short(vb, m, elo >> 24, addr);
                 tmem_ld_wait();
                 tmem_ld_32x32(ta + 160, vb);
-                fold_short(va, m, ehi & 0xffu, Macc, row, slot);
+                fold_short(va, m, ehi & 0xffu, addr);
                 tmem_ld_wait();
                 tmem_ld_32x32(ta + 192, va);
-                fold_short(vb, m, (ehi >> 8) & 0xffu, Macc, row, slot);
+                fold_short(vb, m, (ehi >> 8) & 0xffu, addr);
                 tmem_ld_wait();
                 tmem_ld_32x32(ta + 224, vb);
-                fold_short(va, m, (ehi >> 16) & 0xffu, Macc, row, slot);
+                fold_short(va, m, (ehi >> 16) & 0xffu, addr);
                 tmem_ld_wait();
                 release_accumulator(s, a, lane);
-                fold_short(vb, m, ehi >> 24, Macc, row, slot);
+                fold_short(vb, m, ehi >> 24, addr);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.batch_full[a]);
             }

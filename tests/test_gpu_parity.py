@@ -73,7 +73,8 @@ def test_maxsim_known_answer(mmx_mod):
     assert s.tolist() == [[3.0, 2.0], [0.0, 0.0]]
 
 
-@pytest.mark.parametrize("case", ["t2i_fixed", "ragged_both", "swapped", "single", "many_tiles"])
+@pytest.mark.parametrize("case", ["t2i_fixed", "ragged_both", "swapped", "single", "many_tiles", "swapped_many",
+                                  "short_docs_edge"])
 def test_maxsim_vs_oracle(mmx_mod, case):
     if case == "t2i_fixed":
         docs, queries = synth_colpali(24, 120, doc_len=1030, q_len=(20, 20))
@@ -84,6 +85,22 @@ def test_maxsim_vs_oracle(mmx_mod, case):
         docs, queries = q, d            # images are the MaxSim queries, ragged captions the documents
     elif case == "single":
         docs, queries = synth_colpali(1, 1, doc_len=3, q_len=(1, 1), seed=9)
+    elif case == "swapped_many":
+        # SHORT-document kernel variant over several row-tile pairs and many 256-column tiles; ragged captions make
+        # the reference's zero padding take part in the maxima (d_zero flags)
+        d, q = synth_colpali(40, 1500, doc_len=1030, q_len=(8, 40), seed=13)
+        docs, queries = q, d
+    elif case == "short_docs_edge":
+        # SHORT variant corner cases: 1-row and 3-row documents (padded by repetition), one long document among short
+        # ones, short queries whose segments split 32-row blocks, all-negative similarities against a padded document
+        g = torch.Generator().manual_seed(17)
+        def rnd(n):
+            x = torch.randn(n, 128, generator=g)
+            return (x / x.norm(dim=-1, keepdim=True)).bfloat16()
+        docs = [rnd(int(l)) for l in torch.randint(1, 30, (90,), generator=g)] + [rnd(1), rnd(3), rnd(700), rnd(16), rnd(17)]
+        docs[7] = -docs[7].abs()
+        queries = [rnd(int(l)) for l in torch.randint(1, 50, (37,), generator=g)] + [rnd(300), rnd(129)]
+        queries[3] = queries[3].abs()
     else:
         docs, queries = synth_colpali(300, 700, q_len=(8, 40), ragged_docs=(200, 300), seed=11)
     want = oracle.maxsim_scores(queries, docs)
@@ -130,6 +147,34 @@ def test_maxsim_full_size_properties(mmx_mod):
     Drev = D.view(nd, Ld, 128).flip(0).reshape(-1, 128).contiguous()
     Srev = mmx_mod.ops.maxsim_scores(Q[: 200 * Lq], q_off[:201].clone(), Drev, d_off)
     assert float((Srev.flip(1) - S[:200]).abs().max()) < 1e-4
+
+
+def test_maxsim_i2t_full_size_properties(mmx_mod):
+    """The role-swapped I2T orientation at full size (v28 :375-386 / main.py:622): 5 000 images x 1030 patches as
+    MaxSim queries against 25 000 ragged captions as documents (SHORT-document kernel variant, padding flags on).
+    Size-independent checks: a sub-block rescored alone agrees, and so does the CPU oracle on that sub-block."""
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(4)
+    n_img, n_cap, Lp = 5000, 25000, 1030
+    lens = torch.randint(8, 41, (n_cap,), generator=torch.Generator().manual_seed(5))
+    P = torch.randn(n_img * Lp, 128, generator=g, device=dev)
+    P = (P / P.norm(dim=-1, keepdim=True)).bfloat16()
+    T = torch.randn(int(lens.sum()), 128, generator=g, device=dev)
+    T = (T / T.norm(dim=-1, keepdim=True)).bfloat16()
+    p_off = torch.arange(0, n_img * Lp + 1, Lp, dtype=torch.int32, device=dev)
+    t_off_h = torch.cat([torch.zeros(1, dtype=torch.int64), lens.cumsum(0)])
+    t_off = t_off_h.to(torch.int32).to(dev)
+    flags = torch.from_numpy(oracle.maxsim_pad_flags(lens.numpy())).to(dev)
+    S = mmx_mod.ops.maxsim_scores(P, p_off, T, t_off, flags)
+    assert bool(torch.isfinite(S).all())
+    i0, i1, c0, c1 = 3000, 3003, 12000, 12050                      # c0 is a multiple of the reference's chunk of 10
+    a, b = int(t_off_h[c0]), int(t_off_h[c1])
+    sub_off = (t_off_h[c0:c1 + 1] - a).to(torch.int32).to(dev)
+    sub = mmx_mod.ops.maxsim_scores(P[i0 * Lp:i1 * Lp], p_off[: i1 - i0 + 1].clone(), T[a:b], sub_off, flags[c0:c1].clone())
+    assert float((S[i0:i1, c0:c1] - sub).abs().max()) < 1e-3
+    want = oracle.maxsim_scores(list(P[i0 * Lp:i1 * Lp].cpu().split(Lp)),
+                                list(T[a:b].cpu().split([int(x) for x in lens[c0:c1]])))
+    _assert_close_scores(sub, want)
 
 
 # ----------------------------------------------------------------------------------------------- dense (K1)
