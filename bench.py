@@ -353,10 +353,46 @@ def run_ours(args):
         v, sample = cpu_maxsim_sample(args.cpu_seconds, cores)
         line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
     if not args.no_dense and world == 1:
+        del S, D, Q
+        torch.cuda.empty_cache()
+        line["maxsim_i2t"] = i2t_section(dev, K, W)
         line["dense"] = dense_section(dev, K, W)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def i2t_section(dev, K, W):
+    """The role-swapped orientation of the same model (v28 :375-386 / main.py:622): 5 000 images x 1030 patches are the
+    MaxSim queries, 25 000 captions x 20 tokens the documents — the same 6.6e14 FLOP as the headline step, but a
+    document closes every 20 accumulator columns (SHORT-document kernel variant). Device-resident, CUDA events."""
+    import torch
+    from mmx import ops
+    g = torch.Generator(device=dev).manual_seed(5)
+    n_img, n_cap = ND, NQ
+
+    def unit(x):
+        return x / x.norm(dim=-1, keepdim=True)
+    P = unit(torch.randn(n_img * LD, DIM, generator=g, device=dev)).bfloat16()
+    T = unit(torch.randn(n_cap * LQ, DIM, generator=g, device=dev)).bfloat16()
+    p_off = torch.arange(0, n_img * LD + 1, LD, dtype=torch.int32, device=dev)
+    t_off = torch.arange(0, n_cap * LQ + 1, LQ, dtype=torch.int32, device=dev)
+    out = torch.empty((n_img, n_cap), dtype=torch.float32, device=dev)
+    for _ in range(max(W, 1)):
+        ops.maxsim_scores(P, p_off, T, t_off, None, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        ops.maxsim_scores(P, p_off, T, t_off, None, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    pk = peaks()
+    tf = n_img * n_cap * FLOP_PER_PAIR / (ms * 1e-3) / 1e12
+    return {"workload": "I2T orientation: 5000 images x 1030 patches as MaxSim queries vs 25000 captions x 20 tokens",
+            "ms": ms, "pairs_per_s": n_img * n_cap / (ms * 1e-3), "tflops": tf, "frac_of_bf16_peak": tf / pk["bf16"],
+            "launches_per_call": 5}
 
 
 def dense_section(dev, K, W):

@@ -14,9 +14,13 @@
 // handful of candidates per row (k plus the few extra values sharing a group) and appends them (score, column) to a
 // short per-row list, from which a warp picks the final k.
 //
-// CTA = persistent worker over 128 x 256 output tiles; K streams through a 4-stage TMA ring in 64-wide
-// (128-byte, swizzled) blocks; accumulators ping-pong between TMEM columns [0,256) and [256,512) so the epilogue
-// of tile t overlaps the MMAs of tile t+1. Warp roles: 0 = TMA, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue.
+// CTA = persistent worker over 256 x 256 output tiles = two 128-row halves that share every B block: a 64-wide K block
+// is 2 x 16 KB of A + 32 KB of B for eight 128x256x16 MMAs (1024 clk), i.e. 64 B/clk/SM of L2->SM operand traffic
+// (a 128 x 256 tile needs 96 B/clk/SM and was limited by exactly that, 63-68 % of the bf16 peak). K streams through a
+// 3-stage TMA ring of 128-byte-swizzled blocks; the halves accumulate in TMEM columns [0,256) and [256,512), each
+// with its own full/empty barrier: half 0 finishes 512 clk before half 1, its four epilogue warps drain it while the
+// tensor core is still busy with half 1, and the next tile's half-0 MMAs start as soon as they are done.
+// Warp roles: 0 = TMA, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue of half 0, 8..11 = epilogue of half 1.
 #include <cfloat>
 #include <cuda_bf16.h>
 
@@ -30,12 +34,13 @@
 namespace mmx {
 namespace dense {
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int NSTAGE = 4;
-constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_THREADS = 256;
+constexpr int BM = 128, BN = 256, BK = 64;   // one MMA: 128 rows (TMEM lanes) x 256 columns
+constexpr int TM = 2 * BM;                   // rows of an output tile (two accumulator halves)
+constexpr int NSTAGE = 3;
+constexpr int A_BYTES = BM * 128, B_BYTES = BN * 128, STAGE_BYTES = 2 * A_BYTES + B_BYTES;   // 64 KB
+constexpr int NUM_THREADS = 384;
 constexpr int TMEM_COLS = 512;
-constexpr int BAND = 16;  // row tiles per raster band: concurrent CTAs share A and B tiles through L2
+constexpr long long BAND_BYTES = 32ll << 20;  // rows of Q kept hot in L2 while a band sweeps every column tile
 
 struct Params {
     const int32_t* gt_off;
@@ -58,6 +63,7 @@ struct Params {
     int cand_cap;
     long long nq, ng;
     int kblocks, n_mblk, n_ntile, n_tiles, mode;
+    int band;                   // 256-row tiles per raster band: concurrent CTAs share A and B tiles through L2
 };
 
 struct __align__(1024) Smem {
@@ -68,12 +74,12 @@ struct __align__(1024) Smem {
 };
 
 __device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, int& n_tile) {
-    const int per_band = BAND * p.n_ntile;
+    const int per_band = p.band * p.n_ntile;
     const int band = t / per_band;
     const int rem = t - band * per_band;
-    const int rows = min(BAND, p.n_mblk - band * BAND);
+    const int rows = min(p.band, p.n_mblk - band * p.band);
     n_tile = rem / rows;
-    m_blk = band * BAND + rem % rows;
+    m_blk = band * p.band + rem % rows;
 }
 __device__ __forceinline__ int tile_id(const Params& p, int i) {
     return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i;
@@ -132,8 +138,9 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     const uint32_t st = kc % NSTAGE, ph = (kc / NSTAGE) & 1;
                     mbar_wait(&s.empty[st], ph ^ 1);
                     mbar_arrive_expect_tx(&s.full[st], STAGE_BYTES);
-                    tma_load_2d(s.stage[st], &tmap_q, &s.full[st], kb * BK, m_blk * BM);
-                    tma_load_2d(s.stage[st] + A_BYTES, &tmap_g, &s.full[st], kb * BK, n_tile * BN);
+                    tma_load_2d(s.stage[st], &tmap_q, &s.full[st], kb * BK, m_blk * TM);
+                    tma_load_2d(s.stage[st] + A_BYTES, &tmap_q, &s.full[st], kb * BK, m_blk * TM + BM);
+                    tma_load_2d(s.stage[st] + 2 * A_BYTES, &tmap_g, &s.full[st], kb * BK, n_tile * BN);
                 }
             }
         }
@@ -142,33 +149,38 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
             uint32_t kc = 0, tc = 0;
             for (int i = blockIdx.x; i < n_work; i += gridDim.x, ++tc) {
-                const uint32_t acc = tc & 1, use = tc >> 1;
-                mbar_wait(&s.t_empty[acc], (use & 1) ^ 1);
-                tc_fence_after();
                 for (int kb = 0; kb < p.kblocks; ++kb, ++kc) {
                     const uint32_t st = kc % NSTAGE, ph = (kc / NSTAGE) & 1;
                     mbar_wait(&s.full[st], ph);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(s.stage[st]);
-                    const uint32_t b_addr = a_addr + A_BYTES;
+                    const uint32_t b_addr = a_addr + 2 * A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16_ss(tmem_base + acc * BN, umma_desc_kmajor_sw128(a_addr + k * 32),
-                                     umma_desc_kmajor_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                    for (int h = 0; h < 2; ++h) {
+                        if (kb == 0) {  // the epilogue warps of this half have drained the previous tile
+                            mbar_wait(&s.t_empty[h], (tc & 1) ^ 1);
+                            tc_fence_after();
+                        }
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_ss(tmem_base + h * BN, umma_desc_kmajor_sw128(a_addr + h * A_BYTES + k * 32),
+                                         umma_desc_kmajor_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                        if (kb == p.kblocks - 1) umma_commit(&s.t_full[h]);
+                    }
                     umma_commit(&s.empty[st]);
                 }
-                umma_commit(&s.t_full[acc]);
             }
         }
     } else if (warp >= 4) {
         const int wq = warp & 3;
-        const int row = wq * 32 + lane;
+        const uint32_t acc = (warp - 4) >> 2;  // which 128-row half of every tile this warp drains
+        const int row = acc * BM + wq * 32 + lane;
         uint32_t tc = 0;
         for (int i = blockIdx.x; i < n_work; i += gridDim.x, ++tc) {
             int m_blk, n_tile;
             tile_coords(p, tile_id(p, i), m_blk, n_tile);
-            const uint32_t acc = tc & 1, use = tc >> 1;
-            const long long q = (long long)m_blk * BM + row;
+            const uint32_t use = tc;
+            const long long q = (long long)m_blk * TM + row;
             const long long n0 = (long long)n_tile * BN;
             const bool valid_row = q < p.nq;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BN;
@@ -185,11 +197,20 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             tc_fence_after();
             int cnt = 0;
             float best = -INFINITY;
-#pragma unroll 1
+            uint32_t vbuf[2][32];
+            tmem_ld_32x32(taddr, vbuf[0]);
+#pragma unroll
             for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + ch * 32, v);
+                uint32_t (&v)[32] = vbuf[ch & 1];
                 tmem_ld_wait();
+                if (ch + 1 < BN / 32) {
+                    tmem_ld_32x32(taddr + (ch + 1) * 32, vbuf[(ch + 1) & 1]);  // in flight while this chunk is ranked
+                } else {
+                    // the whole accumulator half is in registers: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s.t_empty[acc]);
+                }
                 const long long c0 = n0 + ch * 32;
                 if (MODE == MMX_MODE_GROUPMAX) {
                     const long long nvalid = p.ng - c0;
@@ -248,9 +269,6 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.t_empty[acc]);
             if (MODE == MMX_MODE_COUNT) {
                 if (valid_row && cnt > 0) atomicAdd(p.cnt_above + q, cnt);
             } else if (MODE == MMX_MODE_GROUPMAX) {
@@ -268,18 +286,18 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 
 // MODE_THRESHOLD work list: ids of the (row tile, column tile) pairs that contain at least one GT column.
 __global__ void gt_tiles_kernel(const int32_t* __restrict__ gt_off, const int32_t* __restrict__ gt_idx, long long nq,
-                                long long ng, long long g_base, int n_mblk, int n_ntile, int32_t* __restrict__ flags,
-                                int32_t* __restrict__ list, int32_t* __restrict__ count) {
+                                long long ng, long long g_base, int n_mblk, int n_ntile, int band_rows,
+                                int32_t* __restrict__ flags, int32_t* __restrict__ list, int32_t* __restrict__ count) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
-    const int m_blk = (int)(q / BM);
-    const int band = m_blk / BAND;
-    const int rows = min(BAND, n_mblk - band * BAND);
+    const int m_blk = (int)(q / TM);
+    const int band = m_blk / band_rows;
+    const int rows = min(band_rows, n_mblk - band * band_rows);
     for (int e = gt_off[q]; e < gt_off[q + 1]; ++e) {
         const long long c = (long long)gt_idx[e] - g_base;
         if (c < 0 || c >= ng) continue;
         const int n_tile = (int)(c / BN);
-        const int t = band * BAND * n_ntile + n_tile * rows + (m_blk - band * BAND);
+        const int t = band * band_rows * n_ntile + n_tile * rows + (m_blk - band * band_rows);
         if (atomicExch(&flags[t], 1) == 0) list[atomicAdd(count, 1)] = t;
     }
 }
@@ -292,7 +310,7 @@ using namespace mmx::dense;
 
 extern "C" int mmx_dense_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes) {
     MMX_REQUIRE(bytes != nullptr, "bytes == NULL");
-    const int64_t tiles = ((nq + BM - 1) / BM) * ((ng + BN - 1) / BN);
+    const int64_t tiles = ((nq + TM - 1) / TM) * ((ng + BN - 1) / BN);
     *bytes = (size_t)tiles * 8 + 512;
     return 0;
 }
@@ -326,7 +344,7 @@ static int launch_dense(const void* Q, int64_t nq, const void* G, int64_t ng, in
 }
 
 static int base_params(Params& p, int64_t nq, int64_t ng, int d) {
-    const long long n_mblk = (nq + BM - 1) / BM, n_ntile = (ng + BN - 1) / BN;
+    const long long n_mblk = (nq + TM - 1) / TM, n_ntile = (ng + BN - 1) / BN;
     MMX_REQUIRE(n_mblk * n_ntile < (1ll << 31), "too many tiles");
     p = Params{};
     p.nq = nq;
@@ -335,6 +353,8 @@ static int base_params(Params& p, int64_t nq, int64_t ng, int d) {
     p.n_mblk = (int)n_mblk;
     p.n_ntile = (int)n_ntile;
     p.n_tiles = (int)(n_mblk * n_ntile);
+    long long band = BAND_BYTES / ((long long)TM * d * 2);
+    p.band = (int)(band < 8 ? 8 : (band > 64 ? 64 : band));
     return 0;
 }
 
@@ -375,7 +395,7 @@ extern "C" int mmx_dense_rank(const void* Q, int64_t nq, const void* G, int64_t 
         int32_t* list = flags + p.n_tiles;
         MMX_CHECK_CUDA(cudaMemsetAsync(count, 0, (size_t)(64 + p.n_tiles) * 4, stream));
         gt_tiles_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(gt_off, gt_idx, nq, ng, g_base, p.n_mblk,
-                                                                          p.n_ntile, flags, list, count);
+                                                                          p.n_ntile, p.band, flags, list, count);
         MMX_CHECK_CUDA(cudaGetLastError());
         p.tile_list = list;
         p.n_tiles_dev = count;
