@@ -162,6 +162,22 @@ int mmx_mt19937_par_set_slack(double rel, double blocks);
 int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t count, int32_t* out, const uint32_t* polys,
                             int n_poly, int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream);
 
+/* The next `count` raw 32-bit outputs of the stream (genrand_int32), produced like K6p; out nullable = only advance
+ * the generator state by `count` words. */
+int mmx_mt19937_raw_par(uint32_t* state, int64_t count, uint32_t* out, const uint32_t* polys, int n_poly,
+                        int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+
+/* K6s  numpy's cumulative in-place shuffles — the `np.random.shuffle(combined)` of main.py:296, P times on the same
+ * array — replayed on the device from raw stream words (legacy RandomState.shuffle: Fisher-Yates from the top,
+ * j = random_interval(i) by masked rejection). words uint32 [n_words] = mmx_mt19937_raw_par output from the current
+ * state; perm int32 [P, n] = the index array after every shuffle (what mmx_perm_stats takes);
+ * info int64 [2] (device): info[1] = number of words the P shuffles consumed, or -1 when n_words was too small (perm
+ * is then unspecified; call again with more words). 2 <= n <= 4096.
+ * workspace: mmx_perm_shuffle_workspace_bytes(n, P, n_words). */
+int mmx_perm_shuffle_workspace_bytes(int n, int P, int64_t n_words, size_t* bytes);
+int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, int P, int32_t* perm, int64_t* info,
+                     void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

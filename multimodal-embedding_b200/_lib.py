@@ -16,7 +16,7 @@ from typing import Optional
 _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 LIB_PATH = CSRC / "libmmx.so"
-SOURCES = ["mmx_host.cu", "maxsim.cu", "dense_rank.cu", "rank_scores.cu", "topk.cu", "stats.cu", "rng.cu"]
+SOURCES = ["mmx_host.cu", "maxsim.cu", "dense_rank.cu", "rank_scores.cu", "topk.cu", "stats.cu", "rng.cu", "shuffle.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -123,6 +123,15 @@ _SIGNATURES = {
     "mmx_mt19937_randint_par": (_c.c_int, [
         _c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p,            # state, high, count, out
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p,   # polys, n_poly, seg_blocks, scratch, bytes, stream
+    ]),
+    "mmx_mt19937_raw_par": (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_void_p,                                     # state, count, out
+        _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p,   # polys, n_poly, seg_blocks, scratch, bytes, stream
+    ]),
+    "mmx_perm_shuffle_workspace_bytes": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int64, _c.POINTER(_c.c_size_t)]),
+    "mmx_perm_shuffle": (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,    # words, n_words, n, P, perm, info
+        _c.c_void_p, _c.c_size_t, _c.c_void_p,                                    # workspace, bytes, stream
     ]),
     "mmx_perm_stats": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,  # combined,n1,n2,perm,P,diffs,stream

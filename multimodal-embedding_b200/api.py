@@ -31,6 +31,7 @@ CSV_COLUMNS = (["Model"] + [f"{k}_{s}" for k in METRIC_KEYS for s in ("mean", "l
                + ["Time", "QPS", "Encoding_Time", "Img_per_sec", "_failure_analysis"])  # main.py:643-665
 N_BOOTSTRAP = 10000       # main.py:265
 CHUNK = 10                # main.py:453
+DEVICE_SHUFFLE_MAX_N = 4096   # permutation tests on longer arrays replay np.random.shuffle on the host (K6s cost ~ n^2)
 DEVICE_RNG = True         # draw the reference's numpy MT19937 stream on the GPU (K6); False = numpy draws on the host
 
 
@@ -240,12 +241,23 @@ def permutation_test(data1: np.ndarray, data2: np.ndarray, n_permutations: int =
     combined = np.concatenate([data1, data2])
     n1, n = len(data1), len(data1) + len(data2)
     r = _rng(rng)
-    idx = np.arange(n, dtype=np.int64)
-    perm = np.empty((n_permutations, n), dtype=np.int32)
-    for p in range(n_permutations):
-        r.shuffle(idx)                                                       # main.py:296
-        perm[p] = idx
-    diffs = ops.perm_stats(_np_h2d(combined, dev, torch.float64), n1, _np_h2d(perm, dev, torch.int32)).cpu().numpy()
+    if DEVICE_RNG and 2 <= n <= DEVICE_SHUFFLE_MAX_N and n_permutations >= 1:
+        # K6s: the shuffles themselves are replayed on the device from numpy's stream; numpy's generator is moved
+        # past exactly the words they consumed
+        drng = r if isinstance(r, ops.DeviceRng) else ops.DeviceRng(r, dev)
+        perm_d = drng.shuffle_indices(n, n_permutations)
+        if drng is not r:
+            drng.commit()
+    else:
+        if isinstance(r, ops.DeviceRng):
+            raise ValueError("arrays this long are shuffled on the host: pass the numpy generator, not a DeviceRng")
+        idx = np.arange(n, dtype=np.int64)
+        perm = np.empty((n_permutations, n), dtype=np.int32)
+        for p in range(n_permutations):
+            r.shuffle(idx)                                                   # main.py:296
+            perm[p] = idx
+        perm_d = _np_h2d(perm, dev, torch.int32)
+    diffs = ops.perm_stats(_np_h2d(combined, dev, torch.float64), n1, perm_d).cpu().numpy()
     return np.mean(diffs >= observed_diff)
 
 

@@ -110,7 +110,7 @@ mt19937_randint_kernel(uint32_t* __restrict__ state, uint32_t rng, uint32_t mask
             if (r < ROUNDS && ((m[j] >> lane) & 1u)) {
                 const int off = base + __popc(m[j] & lt);
                 if ((long long)off < need) {
-                    out[produced + off] = (int32_t)v[j];
+                    if (out != nullptr) out[produced + off] = (int32_t)v[j];
                     if (last_block && (long long)off == need - 1) new_pos_s = r * 32 + lane + 1;
                 }
             }
@@ -362,7 +362,7 @@ mt_par_write_kernel(const ParParams p) {
             if (r < ROUNDS && ((m[j] >> lane) & 1u)) {
                 const int off = bs + __popc(m[j] & lt);
                 if ((long long)off < need) {
-                    p.out[produced + off] = (int32_t)v[j];
+                    if (p.out != nullptr) p.out[produced + off] = (int32_t)v[j];
                     if (last_block && (long long)off == need - 1) stop_pos_s = r * 32 + lane + 1;
                 }
             }
@@ -418,15 +418,10 @@ extern "C" int mmx_mt19937_par_scratch_bytes(int n_poly, size_t* bytes) {
     return 0;
 }
 
-extern "C" int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t count, int32_t* out,
-                                       const uint32_t* polys, int n_poly, int seg_blocks, void* scratch,
-                                       size_t scratch_bytes, cudaStream_t stream) {
+// rng_incl = inclusive maximum of the masked-rejection draw (0xffffffff: every raw word is a value)
+static int par_generate(uint32_t* state, uint32_t rng_incl, int64_t count, int32_t* out, const uint32_t* polys,
+                        int n_poly, int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
     using namespace mmx::rng;
-    MMX_REQUIRE(state != nullptr && (out != nullptr || count == 0) && polys != nullptr && scratch != nullptr,
-                "NULL argument");
-    MMX_REQUIRE(high >= 1 && high <= 0x7fffffffu, "high must be in [1, 2^31)");
-    MMX_REQUIRE(count >= 0 && n_poly >= 1 && seg_blocks >= 1, "bad argument");
-    if (count == 0 || high == 1) return mmx_mt19937_randint(state, high, count, out, stream);
     size_t need = 0;
     mmx_mt19937_par_scratch_bytes(n_poly, &need);
     MMX_REQUIRE(scratch_bytes >= need, "scratch too small: need %zu bytes", need);
@@ -442,7 +437,7 @@ extern "C" int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t c
     p.state = state;
     p.polys = polys;
     p.seg_blocks = seg_blocks;
-    p.rng = high - 1;
+    p.rng = rng_incl;
     p.mask = mask_of(p.rng);
     const size_t smem = (size_t)(XBLOCKS + 2) * N * 4;
     MMX_CHECK_CUDA(cudaFuncSetAttribute(mt_par_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -458,7 +453,7 @@ extern "C" int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t c
         const int64_t c = (count - done < cap_count) ? (count - done) : cap_count;
         int n_seg = (int)(budget_words(p.rng, (double)c) / per_seg) + 1;
         if (n_seg > n_poly + 1) n_seg = n_poly + 1;
-        p.out = out + done;
+        p.out = out != nullptr ? out + done : nullptr;
         p.count = c;
         p.n_seg = n_seg;
         mt_par_expand_kernel<<<1, PTHREADS, 0, stream>>>(p);
@@ -471,4 +466,24 @@ extern "C" int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t c
         done += c;
     }
     return 0;
+}
+
+extern "C" int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t count, int32_t* out,
+                                       const uint32_t* polys, int n_poly, int seg_blocks, void* scratch,
+                                       size_t scratch_bytes, cudaStream_t stream) {
+    MMX_REQUIRE(state != nullptr && (out != nullptr || count == 0) && polys != nullptr && scratch != nullptr,
+                "NULL argument");
+    MMX_REQUIRE(high >= 1 && high <= 0x7fffffffu, "high must be in [1, 2^31)");
+    MMX_REQUIRE(count >= 0 && n_poly >= 1 && seg_blocks >= 1, "bad argument");
+    if (count == 0 || high == 1) return mmx_mt19937_randint(state, high, count, out, stream);
+    return par_generate(state, high - 1, count, out, polys, n_poly, seg_blocks, scratch, scratch_bytes, stream);
+}
+
+extern "C" int mmx_mt19937_raw_par(uint32_t* state, int64_t count, uint32_t* out, const uint32_t* polys, int n_poly,
+                                   int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    MMX_REQUIRE(state != nullptr && polys != nullptr && scratch != nullptr, "NULL argument");
+    MMX_REQUIRE(count >= 0 && n_poly >= 1 && seg_blocks >= 1, "bad argument");
+    if (count == 0) return 0;
+    return par_generate(state, 0xffffffffu, count, reinterpret_cast<int32_t*>(out), polys, n_poly, seg_blocks, scratch,
+                        scratch_bytes, stream);
 }

@@ -1,0 +1,263 @@
+// K6s — numpy's cumulative in-place shuffles (the permutation test) replayed on the device.
+//
+// /root/reference/main.py:295-299 calls np.random.shuffle(combined) 10 000 times on the same array. The legacy
+// RandomState.shuffle of a 1-D array is Fisher-Yates from the top (numpy/random/mtrand.pyx _shuffle_raw):
+//     for i = n-1 .. 1:  j = random_interval(i);  swap(x[i], x[j])
+//     random_interval(max): mask = smallest 2^k - 1 >= max;  do v = next_uint32() & mask; while (v > max)
+// so every step consumes a data-dependent number of 32-bit MT19937 outputs and 2e7 steps form one serial chain
+// (0.27-0.35 s on a host core — ten times the rest of a dense model's statistics on the GPU).
+//
+// The chain is a finite-state transducer: the state is the current `i` in [1, n-1] (n-1 states), the input one
+// random word; a word is accepted iff (w & mask(i)) <= i, and an accept emits j and moves i -> i-1 (wrapping to n-1:
+// next permutation). That parallelises exactly, with the raw word stream W produced by K6p:
+//   B  tables   for every chunk of L words and EVERY start state, count the accepts (one thread per (chunk, state);
+//               the chunk's words sit in shared memory) — (n-1) * |W| steps of ~9 instructions, all independent;
+//   C  chain    one thread walks the chunks: start state and global step offset of each (|W| / L table lookups);
+//   D  emit     one thread per chunk replays it from its now known start state and writes the accepted j values in
+//               step order; the thread that emits the last step reports how many words were consumed;
+//   E  apply    one thread per permutation applies its n-1 swaps to an identity array (column layout [i][P]);
+//   F  compose  idx_p = idx_{p-1} o pi_p in three short phases (blocks of permutations composed independently,
+//               a scan over the block composites, then each block replayed from its prefix): [P, n] index rows,
+//               which is what K5 (mmx_perm_stats) consumes.
+// Bit-exact against numpy by construction; tests/test_gpu_parity.py compares the index rows and the generator state.
+#include "../../include/mmx.h"
+#include "mmx_host.cuh"
+
+namespace mmx {
+namespace shuf {
+
+constexpr int L = 8192;        // words per chunk (accept counts fit uint16)
+constexpr int PB = 64;         // permutations per composition block
+constexpr int MAX_N = 4096;    // work grows with n * |W|; beyond this the host replays the shuffles
+
+struct Plan {
+    long long n_chunks, steps;
+    int n_blocks;
+    size_t off_tab, off_m, off_s, off_j, off_arr, off_pi, off_c, off_d, total;
+};
+
+static Plan make_plan(int n, int P, long long n_words) {
+    Plan pl{};
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    pl.n_chunks = (n_words + L - 1) / L;
+    pl.steps = (long long)P * (n - 1);
+    pl.n_blocks = (P + PB - 1) / PB;
+    size_t o = 256;
+    pl.off_tab = o; o += up((size_t)pl.n_chunks * (n - 1) * 2);   // uint16 accepts per (chunk, start state)
+    pl.off_m = o;   o += up((size_t)(pl.n_chunks + 1) * 4);       // start state of every chunk
+    pl.off_s = o;   o += up((size_t)(pl.n_chunks + 1) * 8);       // global step offset of every chunk
+    pl.off_j = o;   o += up((size_t)pl.steps * 4);                // j of every step
+    pl.off_arr = o; o += up((size_t)n * P * 4);                   // [i][P] working arrays of stage E
+    pl.off_pi = o;  o += up((size_t)n * P * 4);                   // [P][n] pi_p
+    pl.off_c = o;   o += up((size_t)pl.n_blocks * n * 4);         // block composites
+    pl.off_d = o;   o += up((size_t)(pl.n_blocks + 1) * n * 4);   // prefixes of the block composites
+    pl.total = o;
+    return pl;
+}
+
+__device__ __forceinline__ bool step(uint32_t w, int& m, int n1, uint32_t& v) {
+    const uint32_t mask = 0xffffffffu >> __clz(m);   // smallest 2^k - 1 >= m  (m >= 1)
+    v = w & mask;
+    const bool acc = v <= (uint32_t)m;
+    if (acc) m = (m == 1) ? n1 : m - 1;              // the step with max 1 is a permutation's last
+    return acc;
+}
+
+// B: accepts[c][m0-1] for every start state m0 of chunk c
+__global__ void __launch_bounds__(256)
+tables_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, uint16_t* __restrict__ tab) {
+    extern __shared__ uint32_t sw[];
+    const long long c = blockIdx.x;
+    const long long base = c * L;
+    const int len = (int)min((long long)L, n_words - base);
+    for (int t = threadIdx.x; t < len; t += blockDim.x) sw[t] = words[base + t];
+    __syncthreads();
+    const int m0 = blockIdx.y * blockDim.x + threadIdx.x + 1;
+    if (m0 > n1) return;
+    int m = m0, a = 0;
+    uint32_t v;
+#pragma unroll 4
+    for (int t = 0; t < len; ++t) a += step(sw[t], m, n1, v) ? 1 : 0;
+    tab[c * n1 + (m0 - 1)] = (uint16_t)a;
+}
+
+// C: start state / step offset of every chunk; end_chunk = the chunk in which the last step falls (-1: too few words)
+__global__ void chain_kernel(const uint16_t* __restrict__ tab, long long n_chunks, int n1, long long steps,
+                             int32_t* __restrict__ start_m, long long* __restrict__ start_s,
+                             long long* __restrict__ info) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int m = n1;
+    long long s = 0, end_chunk = -1;
+    for (long long c = 0; c < n_chunks; ++c) {
+        start_m[c] = m;
+        start_s[c] = s;
+        const int a = tab[c * n1 + (m - 1)];
+        s += a;
+        if (s >= steps) {
+            end_chunk = c;
+            break;
+        }
+        m = (int)(((long long)(m - 1) - a) % n1);
+        if (m < 0) m += n1;
+        m += 1;
+    }
+    info[0] = end_chunk;
+    info[1] = -1;  // words consumed, written by the emit kernel
+}
+
+// D: replay every chunk from its start state and write the accepted values in step order
+__global__ void __launch_bounds__(64)
+emit_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, long long steps,
+            const int32_t* __restrict__ start_m, const long long* __restrict__ start_s, long long* __restrict__ info,
+            int32_t* __restrict__ jout) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long end_chunk = info[0];
+    if (end_chunk < 0 || c > end_chunk) return;
+    const long long base = c * L;
+    const int len = (int)min((long long)L, n_words - base);
+    int m = start_m[c];
+    long long s = start_s[c];
+    uint32_t v;
+    for (int t = 0; t < len; ++t) {
+        if (step(__ldg(words + base + t), m, n1, v)) {
+            jout[s] = (int32_t)v;
+            if (++s == steps) {
+                info[1] = base + t + 1;  // exactly this many words were consumed
+                return;
+            }
+        }
+    }
+}
+
+// E: thread p applies the swaps of permutation p to an identity array held as column p of arr[i][P]
+__global__ void __launch_bounds__(128)
+apply_kernel(const int32_t* __restrict__ jout, int n, int P, const long long* __restrict__ info,
+             int32_t* __restrict__ arr) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || info[1] < 0) return;  // too few words: jout is incomplete, the caller retries
+    for (int i = 0; i < n; ++i) arr[(long long)i * P + p] = i;
+    const int32_t* jp = jout + (long long)p * (n - 1);
+    for (int i = n - 1; i >= 1; --i) {
+        const int j = jp[n - 1 - i];
+        const int32_t a = arr[(long long)i * P + p], b = arr[(long long)j * P + p];
+        arr[(long long)i * P + p] = b;
+        arr[(long long)j * P + p] = a;
+    }
+}
+
+// [n][P] -> [P][n] through a shared-memory tile
+__global__ void __launch_bounds__(256)
+transpose_kernel(const int32_t* __restrict__ src, int n, int P, int32_t* __restrict__ dst) {
+    __shared__ int32_t tile[32][33];
+    const int i0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8)
+        if (i0 + r < n && p0 + tx < P) tile[r][tx] = src[(long long)(i0 + r) * P + p0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (p0 + r < P && i0 + tx < n) dst[(long long)(p0 + r) * n + i0 + tx] = tile[tx][r];
+}
+
+// F1 / F3: CTA b composes the permutations of its block in order, starting from `start` (nullptr = identity);
+// write_rows = 1 stores every intermediate row (the result), 0 stores only the block composite.
+__global__ void __launch_bounds__(512)
+compose_block_kernel(const int32_t* __restrict__ pi, int n, int P, const int32_t* __restrict__ start,
+                     int32_t* __restrict__ comp_out, int32_t* __restrict__ rows_out) {
+    extern __shared__ int32_t sm[];
+    int32_t* cur = sm;
+    int32_t* nxt = sm + n;
+    const int b = blockIdx.x;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) cur[k] = start != nullptr ? start[(long long)b * n + k] : k;
+    __syncthreads();
+    const int p_end = min(P, (b + 1) * PB);
+    for (int p = b * PB; p < p_end; ++p) {
+        const int32_t* row = pi + (long long)p * n;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int32_t x = cur[row[k]];
+            nxt[k] = x;
+            if (rows_out != nullptr) rows_out[(long long)p * n + k] = x;
+        }
+        __syncthreads();
+        int32_t* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    if (comp_out != nullptr)
+        for (int k = threadIdx.x; k < n; k += blockDim.x) comp_out[(long long)b * n + k] = cur[k];
+}
+
+// F2: prefix[b] = state before block b (prefix[0] = identity, prefix[b+1] = prefix[b] o comp[b])
+__global__ void __launch_bounds__(512)
+compose_scan_kernel(const int32_t* __restrict__ comp, int n, int n_blocks, int32_t* __restrict__ prefix) {
+    extern __shared__ int32_t sm[];
+    int32_t* cur = sm;
+    int32_t* nxt = sm + n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        cur[k] = k;
+        prefix[k] = k;
+    }
+    __syncthreads();
+    for (int b = 0; b < n_blocks; ++b) {
+        const int32_t* c = comp + (long long)b * n;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const int32_t x = cur[c[k]];
+            nxt[k] = x;
+            prefix[(long long)(b + 1) * n + k] = x;
+        }
+        __syncthreads();
+        int32_t* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+}
+
+}  // namespace shuf
+}  // namespace mmx
+
+using namespace mmx;
+using namespace mmx::shuf;
+
+extern "C" int mmx_perm_shuffle_workspace_bytes(int n, int P, int64_t n_words, size_t* bytes) {
+    MMX_REQUIRE(bytes != nullptr && n >= 2 && n <= MAX_N && P >= 1 && n_words >= 1, "bad argument (2 <= n <= %d)", MAX_N);
+    *bytes = make_plan(n, P, n_words).total;
+    return 0;
+}
+
+extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, int P, int32_t* perm, int64_t* info,
+                                void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    MMX_REQUIRE(words != nullptr && perm != nullptr && info != nullptr && workspace != nullptr, "NULL argument");
+    MMX_REQUIRE(n >= 2 && n <= MAX_N && P >= 1 && n_words >= 1, "bad argument (2 <= n <= %d)", MAX_N);
+    const Plan pl = make_plan(n, P, n_words);
+    MMX_REQUIRE(workspace_bytes >= pl.total, "workspace too small: need %zu bytes", pl.total);
+    MMX_REQUIRE(pl.n_chunks < (1ll << 31), "too many chunks");
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    uint16_t* tab = reinterpret_cast<uint16_t*>(ws + pl.off_tab - 256);
+    int32_t* start_m = reinterpret_cast<int32_t*>(ws + pl.off_m - 256);
+    long long* start_s = reinterpret_cast<long long*>(ws + pl.off_s - 256);
+    int32_t* jout = reinterpret_cast<int32_t*>(ws + pl.off_j - 256);
+    int32_t* arr = reinterpret_cast<int32_t*>(ws + pl.off_arr - 256);
+    int32_t* pi = reinterpret_cast<int32_t*>(ws + pl.off_pi - 256);
+    int32_t* comp = reinterpret_cast<int32_t*>(ws + pl.off_c - 256);
+    int32_t* prefix = reinterpret_cast<int32_t*>(ws + pl.off_d - 256);
+    const int n1 = n - 1;
+    dim3 gb((unsigned)pl.n_chunks, (unsigned)((n1 + 255) / 256));
+    tables_kernel<<<gb, 256, L * 4, stream>>>(words, n_words, n1, tab);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    chain_kernel<<<1, 32, 0, stream>>>(tab, pl.n_chunks, n1, pl.steps, start_m, start_s,
+                                       reinterpret_cast<long long*>(info));
+    emit_kernel<<<(unsigned)((pl.n_chunks + 63) / 64), 64, 0, stream>>>(words, n_words, n1, pl.steps, start_m, start_s,
+                                                                       reinterpret_cast<long long*>(info), jout);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    // when the words did not suffice (info[1] = -1) the swaps are skipped and the stages below shuffle unspecified
+    // but in-range index rows; the caller checks info[1] before using `perm` and retries with a longer stream
+    MMX_CHECK_CUDA(cudaMemsetAsync(arr, 0, (size_t)n * P * 4, stream));
+    apply_kernel<<<(P + 127) / 128, 128, 0, stream>>>(jout, n, P, reinterpret_cast<const long long*>(info), arr);
+    dim3 gt((unsigned)((P + 31) / 32), (unsigned)((n + 31) / 32));
+    transpose_kernel<<<gt, 256, 0, stream>>>(arr, n, P, pi);
+    const size_t smem = (size_t)n * 8;
+    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, nullptr, comp, nullptr);
+    compose_scan_kernel<<<1, 512, smem, stream>>>(comp, n, pl.n_blocks, prefix);
+    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, prefix, nullptr, perm);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -324,6 +324,53 @@ class DeviceRng:
                                                       _stream()))
         return out
 
+    def raw_words(self, count: int, advance: bool = True) -> Optional[torch.Tensor]:
+        """The next `count` raw 32-bit outputs (as int32 bit patterns). advance=False leaves the generator where it
+        is (the draws are made from a copy of the state); ``skip`` then moves it by the number actually consumed."""
+        from . import mtjump
+        polys, scratch = self._par_buffers()
+        st = self.state if advance else self.state.clone()
+        out = torch.empty((count,), dtype=torch.int32, device=self.state.device)
+        _lib.check(_lib.lib().mmx_mt19937_raw_par(st.data_ptr(), int(count), out.data_ptr(), polys.data_ptr(),
+                                                  mtjump.N_POLY, mtjump.SEG_BLOCKS, scratch.data_ptr(),
+                                                  scratch.numel(), _stream()))
+        return out
+
+    def skip(self, count: int) -> None:
+        """Advance the generator by `count` raw words without materialising them."""
+        from . import mtjump
+        polys, scratch = self._par_buffers()
+        _lib.check(_lib.lib().mmx_mt19937_raw_par(self.state.data_ptr(), int(count), None, polys.data_ptr(),
+                                                  mtjump.N_POLY, mtjump.SEG_BLOCKS, scratch.data_ptr(),
+                                                  scratch.numel(), _stream()))
+
+    def shuffle_indices(self, n: int, n_shuffles: int) -> torch.Tensor:
+        """K6s. int32 CUDA [n_shuffles, n]: an index array after each of `n_shuffles` cumulative in-place
+        ``shuffle`` calls (legacy RandomState.shuffle, main.py:296), consuming exactly the words numpy would."""
+        h = _lib.lib()
+        dev = self.state.device
+        # words a shuffle of n items needs: step i accepts with probability (i + 1) / 2^ceil(log2(i + 1))
+        i = np.arange(1, n, dtype=np.float64)
+        pacc = (i + 1.0) / np.exp2(np.ceil(np.log2(i + 1.0)))
+        mean = n_shuffles * float(np.sum(1.0 / pacc))
+        sigma = float(np.sqrt(n_shuffles * np.sum((1.0 - pacc) / pacc ** 2)))
+        n_words = int(mean + 8.0 * sigma) + 2048
+        perm = torch.empty((n_shuffles, n), dtype=torch.int32, device=dev)
+        info = torch.empty((2,), dtype=torch.int64, device=dev)
+        while True:
+            words = self.raw_words(n_words, advance=False)
+            need = ctypes.c_size_t()
+            _lib.check(h.mmx_perm_shuffle_workspace_bytes(n, n_shuffles, n_words, ctypes.byref(need)))
+            ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+            _lib.check(h.mmx_perm_shuffle(words.data_ptr(), n_words, n, n_shuffles, perm.data_ptr(), info.data_ptr(),
+                                          ws.data_ptr(), need.value, _stream()))
+            consumed = int(info[1].item())
+            if consumed >= 0:
+                break
+            n_words = int(n_words * 1.25)          # 8 sigma was not enough: replay with a longer stream
+        self.skip(consumed)
+        return perm
+
     def commit(self) -> None:
         host = self.state.cpu().numpy().view(np.uint32)
         st = self.source.get_state()

@@ -429,6 +429,59 @@ def test_device_rng_jump_ahead_starved_budget(mmx_mod):
     assert rs_dev.randint(0, 1 << 30) == rs_ref.randint(0, 1 << 30)
 
 
+@pytest.mark.parametrize("n,n_shuffles", [(2, 9), (3, 40), (5, 300), (64, 120), (600, 300), (2000, 150), (4096, 12)])
+def test_device_shuffle_matches_numpy_cumulative_shuffles(mmx_mod, n, n_shuffles):
+    """K6s: the index array after every one of numpy's cumulative in-place shuffles (main.py:296), the number of
+    stream words they consumed, and the generator state afterwards — bit for bit."""
+    rs_dev, rs_ref = np.random.RandomState(4321), np.random.RandomState(4321)
+    for r in (rs_dev, rs_ref):
+        r.randint(0, 9, size=333)                         # start inside a 624-word block
+    d = mmx_mod.ops.DeviceRng(rs_dev)
+    got = d.shuffle_indices(n, n_shuffles).cpu().numpy()
+    tail = d.randint(1000, 50).cpu().numpy()              # the stream continues right after the shuffles
+    d.commit()
+    idx = np.arange(n)
+    want = np.empty((n_shuffles, n), dtype=np.int64)
+    for k in range(n_shuffles):
+        rs_ref.shuffle(idx)
+        want[k] = idx
+    assert np.array_equal(got.astype(np.int64), want)
+    assert np.array_equal(tail.astype(np.int64), rs_ref.randint(0, 1000, size=50))
+    a, b = rs_dev.get_state(), rs_ref.get_state()
+    assert np.array_equal(a[1], b[1]) and a[2:] == b[2:]
+
+
+def test_device_shuffle_reports_short_stream(mmx_mod):
+    """With too few words the library says so (info[1] = -1) instead of returning a wrong permutation."""
+    import ctypes
+    dev = _dev()
+    h = mmx_mod._lib.lib()
+    d = mmx_mod.ops.DeviceRng(np.random.RandomState(1))
+    n, P, n_words = 100, 50, 3000                          # 50 shuffles of 100 items need ~6000 words
+    words = d.raw_words(n_words, advance=False)
+    need = ctypes.c_size_t()
+    mmx_mod._lib.check(h.mmx_perm_shuffle_workspace_bytes(n, P, n_words, ctypes.byref(need)))
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    perm = torch.empty((P, n), dtype=torch.int32, device=dev)
+    info = torch.zeros(2, dtype=torch.int64, device=dev)
+    mmx_mod._lib.check(h.mmx_perm_shuffle(words.data_ptr(), n_words, n, P, perm.data_ptr(), info.data_ptr(),
+                                          ws.data_ptr(), need.value, torch.cuda.current_stream().cuda_stream))
+    assert int(info[1].item()) == -1
+    # raw words are numpy's own 32-bit outputs
+    assert np.array_equal(words.cpu().numpy().view(np.uint32),
+                          np.random.RandomState(1)._bit_generator.random_raw(n_words).astype(np.uint32))
+
+
+def test_permutation_test_long_arrays_fall_back_to_host_shuffles(mmx_mod, monkeypatch):
+    monkeypatch.setattr(mmx_mod.api, "DEVICE_SHUFFLE_MAX_N", 100)
+    rs = np.random.RandomState(3)
+    d1, d2 = rs.normal(size=90), rs.normal(0.1, 1.0, size=80)
+    p_host = mmx_mod.permutation_test(d1, d2, 300, rng=np.random.RandomState(8))
+    monkeypatch.setattr(mmx_mod.api, "DEVICE_SHUFFLE_MAX_N", 4096)
+    p_dev = mmx_mod.permutation_test(d1, d2, 300, rng=np.random.RandomState(8))
+    assert p_host == p_dev == oracle.permutation_test(d1, d2, 300, rng=np.random.RandomState(8))
+
+
 def test_device_rng_global_stream_and_host_mode_agree(mmx_mod, golden_dir, monkeypatch):
     """bootstrap_confidence_interval on the GLOBAL np.random stream: device-drawn (default) and host-drawn index
     streams give the same tuple and leave np.random in the same state as the reference's 10 000 choice() calls."""
