@@ -356,7 +356,7 @@ def run_ours(args):
         del S, D, Q
         torch.cuda.empty_cache()
         line["maxsim_i2t"] = i2t_section(dev, K, W)
-        line["dense"] = dense_section(dev, K, W)
+        line["dense"] = dense_section(dev, K, W, cpu_iters=0 if args.no_cpu_baseline else 2)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -395,7 +395,7 @@ def i2t_section(dev, K, W):
             "launches_per_call": 5}
 
 
-def dense_section(dev, K, W):
+def dense_section(dev, K, W, cpu_iters=2):
     """BASELINE.json configs[1]: SigLIP-400M shapes 5000x1152 / 25000x1152, three protocols + 1000-iteration
     bootstrap + nine CIs (+ one permutation test), device-resident and end to end."""
     import numpy as np
@@ -444,7 +444,21 @@ def dense_section(dev, K, W):
                              rng=np.random.RandomState(7))
     perm_ms = 1e3 * (time.perf_counter() - t0)
     pairs = N * N * 2 + N * 5 * N
-    return {"workload": "SigLIP-400M dense scoring 5000x1152 / 25000x1152, T2I + I2T(1-to-5) + I2T_Sym, "
+    # the reference's CPU path for the same row (oracle port of main.py:586-634: gather, rescore, 45 000 torch.topk
+    # calls per iteration), bounded: 2 of the 1000 iterations, the per-iteration cost extrapolated
+    cpu = None
+    if cpu_iters > 0:
+        import oracle
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        per = oracle.bootstrap_rescore_reference(img, t2i, all_txt, cpu_iters, rng=np.random.RandomState(42))
+        cpu_s = (time.perf_counter() - t0) / cpu_iters
+        same = all(per[i][k] == row["_bootstrap_values"][k][i] for i in range(cpu_iters) for k in mmx.METRIC_KEYS)
+        cpu = {"kind": "port", "cores": os.cpu_count() or 1, "s_per_iteration": cpu_s,
+               "sample": f"{cpu_iters} of {N_ITER} bootstrap iterations (gather + rescore + compute_metrics_detailed)",
+               "extrapolated_s_for_1000_iterations": cpu_s * N_ITER,
+               "first_iterations_equal_gpu_row": bool(same)}
+    return {"cpu_baseline": cpu, "workload": "SigLIP-400M dense scoring 5000x1152 / 25000x1152, T2I + I2T(1-to-5) + I2T_Sym, "
                         "1000-iter bootstrap + 9 CIs (10 000 resamples each)",
             "metric": "dense_score_rank_bootstrap_wall_ms", "device_resident_ms": dev_ms, "e2e_ms": e2e_ms,
             "e2e_note": "mmx.run_bootstrap_from_embeddings from pinned host tensors to the 42-column row; the "
