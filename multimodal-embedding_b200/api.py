@@ -409,6 +409,25 @@ class FlatMultiVector:
         off[1:] = np.cumsum(self.lens)
         return _h2d(_as_bf16(self.flat, "multi-vector embeddings"), dev), _np_h2d(off, dev, torch.int32)
 
+    def to_list(self) -> List[torch.Tensor]:
+        """The reference's representation: a python list of [L_i, 128] tensors (views, no copy)."""
+        return list(self.flat.split([int(l) for l in self.lens]))
+
+    def save(self, path: str) -> None:
+        """On-disk cache: the reference persists no embeddings, so every rerun of the statistics pays
+        for the encoders again. One .npz: the bf16 rows as their uint16 bit patterns plus the lengths."""
+        flat = _as_bf16(self.flat, "multi-vector embeddings").detach().cpu().contiguous()
+        np.savez(path, bits=flat.view(torch.int16).numpy().view(np.uint16), lens=self.lens,
+                 dim=np.int64(flat.shape[1] if flat.dim() == 2 else 0))
+
+    @staticmethod
+    def load(path: str, pin: bool = True) -> "FlatMultiVector":
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        flat = torch.from_numpy(z["bits"].view(np.int16).copy()).view(torch.bfloat16)
+        if pin and torch.cuda.is_available():
+            flat = flat.pin_memory()           # so the upload overlaps the scoring (_maxsim_streamed)
+        return FlatMultiVector(flat, z["lens"])
+
 
 H2D_DOC_CHUNKS = 8   # host-resident documents are uploaded in this many pieces, each scored while the next one copies
 

@@ -65,3 +65,16 @@ def test_no_cpu_fallback():
         mmx.bootstrap_confidence_interval(np.arange(10.0))
     with pytest.raises(mmx.MmxError):
         mmx.ops.dense_scores(img, img)
+
+
+def test_flat_multivector_disk_cache_roundtrip(tmp_path):
+    g = torch.Generator().manual_seed(0)
+    items = [torch.randn(int(l), 128, generator=g).bfloat16() for l in (3, 1, 17, 1030, 0, 5)]
+    fv = mmx.FlatMultiVector.from_list(items)
+    fv.save(str(tmp_path / "emb"))
+    back = mmx.FlatMultiVector.load(str(tmp_path / "emb"), pin=False)
+    assert list(back.lens) == [3, 1, 17, 1030, 0, 5] and back.flat.dtype == torch.bfloat16
+    assert torch.equal(back.flat.view(torch.int16), fv.flat.view(torch.int16))
+    assert all(torch.equal(a.view(torch.int16), b.view(torch.int16)) for a, b in zip(back.to_list(), items))
+    part = back.slice(2, 4)
+    assert len(part) == 2 and part.flat.shape[0] == 17 + 1030
