@@ -322,6 +322,16 @@ def bootstrap_from_ranks(ranks: Dict[str, ops.ProtocolRanks], sample_indices: np
     """K3: int64 [B, 9] correct counts (METRIC_KEYS order) for the reference's resample draws
     ``sample_indices`` [B, N] (main.py:588), without rescoring. With want_hits also returns, per base T2I query,
     (R@1 hits summed over iterations, times drawn) — the inputs of aggregate_failure_analysis."""
+    correct, hits, drawn = _bootstrap_counts_device(ranks, sample_indices, n_images, want_hits)
+    correct = correct.cpu().numpy().astype(np.int64)
+    if want_hits:
+        return correct, hits.cpu().numpy().astype(np.int64), drawn.cpu().numpy()
+    return correct
+
+
+def _bootstrap_counts_device(ranks: Dict[str, ops.ProtocolRanks], sample_indices, n_images: int, want_hits: bool):
+    """bootstrap_from_ranks without the device->host copies: (int32 CUDA [B, 9], hits int32 [nq] | None,
+    drawn int64 [nq] | None)."""
     dev = _device()
     if isinstance(sample_indices, torch.Tensor) and sample_indices.is_cuda:
         si = sample_indices.to(torch.int32)
@@ -332,13 +342,12 @@ def bootstrap_from_ranks(ranks: Dict[str, ops.ProtocolRanks], sample_indices: np
     hits = torch.zeros(ranks["T2I"].nq, dtype=torch.int32, device=dev) if want_hits else None
     for name in ("T2I", "I2T", "I2T_Sym"):
         cols.append(ops.boot_counts(ranks[name], mult, q_hits1=hits if name == "T2I" else None))
-    correct = torch.cat(cols, dim=1).cpu().numpy().astype(np.int64)
+    drawn = None
     if want_hits:
         drawn = mult.sum(dim=0, dtype=torch.int64)
         qu = ranks["T2I"].q_unit
         drawn = drawn if qu is None else drawn[qu.long()]
-        return correct, hits.cpu().numpy().astype(np.int64), drawn.cpu().numpy()
-    return correct
+    return torch.cat(cols, dim=1), hits, drawn
 
 
 def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, n_iterations: int,
@@ -350,24 +359,59 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     keys in insertion order 10 000 x choice(values, n_iterations)."""
     t0 = time.time() if t_start is None else t_start
     n_images = len(img_embeds)
-    ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info)
-    drng = ops.DeviceRng(_rng(rng)) if DEVICE_RNG else None
-    if drng is not None:
-        sample_indices = drng.randint(n_images, n_iterations * n_images).view(n_iterations, n_images)   # main.py:588
-    else:
-        sample_indices = _rng(rng).randint(0, n_images, size=(n_iterations, n_images))
-    correct, hits, drawn = bootstrap_from_ranks(ranks, sample_indices, n_images, want_hits=True)
-    values = 100.0 * correct / n_images                                                    # main.py:358,368,378
-    torch.cuda.synchronize()
-    total_time = time.time() - t0                                                          # main.py:636
     aggregated: Dict[str, Any] = {"Model": m_info["name"]}
-    for j, key in enumerate(METRIC_KEYS):                                                  # main.py:644-651
-        v = np.ascontiguousarray(values[:, j])
-        mean, lower, upper = bootstrap_confidence_interval(v, rng=drng if drng is not None else rng)
-        aggregated[f"{key}_mean"] = mean
-        aggregated[f"{key}_lower"] = lower
-        aggregated[f"{key}_upper"] = upper
-        aggregated[f"{key}_std"] = np.std(v)
+    drng = None
+    if DEVICE_RNG:
+        # The draws do not depend on the scores: the whole numpy stream of this row — n_iterations x choice(N, N), then
+        # nine times 10 000 x choice(values, n_iterations), consecutive in the stream — is regenerated on a side stream
+        # (K6p) while the embeddings cross PCIe and K1 runs; the nine CI kernels then run back to back on device-resident
+        # values and ONE device->host copy brings everything back.
+        dev = _device()
+        main = torch.cuda.current_stream()
+        side = _aux_stream(dev, "rng")
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            drng = ops.DeviceRng(_rng(rng), dev)
+            sample_indices = drng.randint(n_images, n_iterations * n_images).view(n_iterations, n_images)  # main.py:588
+            ci_idx = drng.randint(n_iterations, len(METRIC_KEYS) * N_BOOTSTRAP * n_iterations).view(
+                len(METRIC_KEYS), N_BOOTSTRAP, n_iterations)                                            # main.py:269
+            rng_done = torch.cuda.Event()
+            rng_done.record(side)
+        ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info)
+        main.wait_event(rng_done)
+        for t in (sample_indices, ci_idx):
+            t.record_stream(main)
+        correct_d, hits_d, drawn_d = _bootstrap_counts_device(ranks, sample_indices, n_images, want_hits=True)
+        n_t = torch.tensor(float(n_images), dtype=torch.float64, device=dev)
+        values_d = 100.0 * correct_d.to(torch.float64) / n_t          # tensor / tensor: IEEE division, as numpy's
+        done = torch.cuda.Event()
+        done.record(main)
+        means_d = torch.stack([ops.ci_means(values_d[:, j].contiguous(), ci_idx[j]) for j in range(len(METRIC_KEYS))])
+        done.synchronize()
+        total_time = time.time() - t0                                                      # main.py:636
+        values, means = values_d.cpu().numpy(), means_d.cpu().numpy()
+        hits, drawn = hits_d.cpu().numpy().astype(np.int64), drawn_d.cpu().numpy()
+        alpha = (1 - 0.95) / 2
+        for j, key in enumerate(METRIC_KEYS):                                              # main.py:644-651, :259-278
+            v = np.ascontiguousarray(values[:, j])
+            aggregated[f"{key}_mean"] = np.mean(v)
+            aggregated[f"{key}_lower"] = np.percentile(means[j], alpha * 100)
+            aggregated[f"{key}_upper"] = np.percentile(means[j], (1 - alpha) * 100)
+            aggregated[f"{key}_std"] = np.std(v)
+    else:
+        ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info)
+        sample_indices = _rng(rng).randint(0, n_images, size=(n_iterations, n_images))
+        correct, hits, drawn = bootstrap_from_ranks(ranks, sample_indices, n_images, want_hits=True)
+        values = 100.0 * correct / n_images                                                # main.py:358,368,378
+        torch.cuda.synchronize()
+        total_time = time.time() - t0                                                      # main.py:636
+        for j, key in enumerate(METRIC_KEYS):                                              # main.py:644-651
+            v = np.ascontiguousarray(values[:, j])
+            mean, lower, upper = bootstrap_confidence_interval(v, rng=rng)
+            aggregated[f"{key}_mean"] = mean
+            aggregated[f"{key}_lower"] = lower
+            aggregated[f"{key}_upper"] = upper
+            aggregated[f"{key}_std"] = np.std(v)
     enc = encoding_time if encoding_time > 0 else float("nan")
     aggregated["Time"] = total_time
     aggregated["QPS"] = n_images / enc
