@@ -42,6 +42,7 @@
 // of a whole tile's documents at once, one lane per document, instead of one latency-bound shuffle tree per document.
 #include <cfloat>
 #include <climits>
+#include <cstdlib>
 
 #include "../../include/mmx.h"
 #include "mmx_host.cuh"
@@ -893,7 +894,12 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
     // Chunk of whole documents per work item: small enough to stay L2-resident while all row-tile pairs sweep it,
     // and numerous enough that the persistent grid is balanced (>= 32 items per SM when the problem allows).
     const long long avg_doc_bytes = (n_dtok * (long long)DIM * 2 + nd - 1) / nd;
-    long long dpc = L2_CHUNK_BYTES / (avg_doc_bytes > 0 ? avg_doc_bytes : 1);
+    long long chunk_bytes = L2_CHUNK_BYTES;
+    if (const char* e = getenv("MMX_L2_CHUNK_MB")) {  // tuning knob (dev/tune_chunk.sh); unset in production
+        const long long mb = atoll(e);
+        if (mb >= 1 && mb <= 4096) chunk_bytes = mb << 20;
+    }
+    long long dpc = chunk_bytes / (avg_doc_bytes > 0 ? avg_doc_bytes : 1);
     const long long want_chunks = ((long long)sms * 32 + p.n_mpairs - 1) / p.n_mpairs;
     const long long dpc_balance = (nd + want_chunks - 1) / want_chunks;
     if (dpc > dpc_balance) dpc = dpc_balance;
