@@ -135,6 +135,10 @@ int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_above, cons
  * idx int32 [R, n] is the reference's index stream (RandomState.randint(0, n, (R, n)) == R x choice);
  * means[r] = np.mean(data[idx[r]]) bit for bit (fp64, numpy's pairwise summation order). */
 int mmx_ci_means(const double* data, int n, const int32_t* idx, int R, double* means, cudaStream_t stream);
+/* The same for `batch` independent data vectors in one launch (the nine metric keys of a CSV row, main.py:644-651):
+ * data [batch, n], idx [batch, R, n], means [batch, R]. */
+int mmx_ci_means_batched(const double* data, int n, const int32_t* idx, int R, int batch, double* means,
+                         cudaStream_t stream);
 
 /* K5  permutation statistics — replaces the shuffle + two means loop of main.py:295-299.
  * perm int32 [P, n1+n2] are the cumulative np.random.shuffle states of an index array;

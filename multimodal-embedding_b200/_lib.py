@@ -117,6 +117,9 @@ _SIGNATURES = {
     "mmx_ci_means": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,   # data, n, idx, R, means, stream
     ]),
+    "mmx_ci_means_batched": (_c.c_int, [
+        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,   # data, n, idx, R, batch, means, stream
+    ]),
     "mmx_mt19937_randint": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p, _c.c_void_p]),
     "mmx_mt19937_par_scratch_bytes": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_size_t)]),
     "mmx_mt19937_par_set_slack": (_c.c_int, [_c.c_double, _c.c_double]),

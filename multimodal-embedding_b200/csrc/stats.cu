@@ -203,6 +203,10 @@ gather_mean_kernel(const double* __restrict__ data, int n_data, const int32_t* _
                    int n1, int n2, const __grid_constant__ Program p1, const __grid_constant__ Program p2,
                    int data_in_smem, double* __restrict__ out) {
     extern __shared__ double sm_data[];
+    // blockIdx.y = batch entry (its own data vector, index rows and outputs): nine CIs of a row in one launch
+    data += (long long)blockIdx.y * n_data;
+    idx += (long long)blockIdx.y * R * ld;
+    out += (long long)blockIdx.y * R;
     const double* d = data;
     if (data_in_smem) {
         for (int i = threadIdx.x; i < n_data; i += blockDim.x) sm_data[i] = data[i];
@@ -272,8 +276,9 @@ extern "C" int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_
 }
 
 static int launch_gather_mean(const double* data, int n_data, const int32_t* idx, int64_t ld, int R, int n1, int n2,
-                              double* out, cudaStream_t stream) {
+                              double* out, cudaStream_t stream, int batch = 1) {
     MMX_REQUIRE(n1 >= 1 && n2 >= 0 && ld >= (int64_t)n1 + n2, "bad segment sizes");
+    MMX_REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
     if (R == 0) return 0;
     Program p1, p2;
     if (make_program(n1, &p1) != 0) return -2;
@@ -286,13 +291,19 @@ static int launch_gather_mean(const double* data, int n_data, const int32_t* idx
         MMX_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         smem_set = 200 * 1024;
     }
-    gather_mean_kernel<<<(R + 127) / 128, 128, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, p1, p2, in_smem, out);
+    gather_mean_kernel<<<dim3((R + 127) / 128, batch), 128, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, p1, p2,
+                                                                            in_smem, out);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int mmx_ci_means(const double* data, int n, const int32_t* idx, int R, double* means, cudaStream_t stream) {
     return launch_gather_mean(data, n, idx, n, R, n, 0, means, stream);
+}
+
+extern "C" int mmx_ci_means_batched(const double* data, int n, const int32_t* idx, int R, int batch, double* means,
+                                    cudaStream_t stream) {
+    return launch_gather_mean(data, n, idx, n, R, n, 0, means, stream, batch);
 }
 
 extern "C" int mmx_perm_stats(const double* combined, int n1, int n2, const int32_t* perm, int P, double* diffs,

@@ -263,6 +263,20 @@ def ci_means(data: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def ci_means_batched(data: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """K4 for several data vectors at once. data fp64 CUDA [M, n], idx int32 CUDA [M, R, n] -> fp64 CUDA [M, R]."""
+    _need_cuda(data, idx)
+    if data.dtype != torch.float64 or idx.dtype != torch.int32:
+        raise TypeError("ci_means_batched takes fp64 data and int32 indices")
+    data, idx = data.contiguous(), idx.contiguous()
+    M, R, n = idx.shape
+    if tuple(data.shape) != (M, n):
+        raise ValueError("data must be [M, n] for idx [M, R, n]")
+    out = torch.empty((M, R), dtype=torch.float64, device=data.device)
+    _lib.check(_lib.lib().mmx_ci_means_batched(data.data_ptr(), n, idx.data_ptr(), R, M, out.data_ptr(), _stream()))
+    return out
+
+
 def perm_stats(combined: torch.Tensor, n1: int, perm: torch.Tensor) -> torch.Tensor:
     """K5. combined fp64 CUDA [n1+n2], perm int32 CUDA [P, n1+n2] -> fp64 CUDA [P] |mean(first n1) - mean(rest)|."""
     _need_cuda(combined, perm)

@@ -368,6 +368,18 @@ def test_ci_means_bit_exact_any_length(mmx_mod, n):
             assert np.array_equal(d, w)
 
 
+def test_ci_means_batched_equals_single_launches(mmx_mod):
+    dev = _dev()
+    rs = np.random.RandomState(2)
+    data = torch.from_numpy(np.round(rs.normal(40, 1, size=(9, 1000)) * 50) / 50).to(dev)
+    idx = torch.from_numpy(rs.randint(0, 1000, size=(9, 300, 1000)).astype(np.int32)).to(dev)
+    got = mmx_mod.ops.ci_means_batched(data, idx)
+    for j in range(9):
+        assert torch.equal(got[j], mmx_mod.ops.ci_means(data[j].contiguous(), idx[j].contiguous()))
+    want = np.array([[np.mean(data[j].cpu().numpy()[idx[j, r].cpu().numpy()]) for r in range(5)] for j in range(9)])
+    assert np.array_equal(got[:, :5].cpu().numpy(), want)
+
+
 # ----------------------------------------------------------------------------------------------- numpy stream on the device (K6)
 @pytest.mark.parametrize("high", [2, 3, 1000, 5000, 25000, 100000, 1 << 20, (1 << 31) - 1])
 def test_device_rng_matches_numpy_stream(mmx_mod, high):
