@@ -102,6 +102,14 @@ def _flatten(items: List[torch.Tensor], dev: torch.device) -> Tuple[torch.Tensor
     return _h2d(flat, dev), _np_h2d(off, dev, torch.int32), lens
 
 
+def _flatten_any(x, dev: torch.device) -> Tuple[torch.Tensor, torch.Tensor, np.ndarray]:
+    """Lists / padded tensors (the reference's representations) or a FlatMultiVector (no 30 000-tensor torch.cat)."""
+    if isinstance(x, FlatMultiVector):
+        flat, off = x.to_device(dev)
+        return flat, off, x.lens
+    return _flatten(_as_list(x), dev)
+
+
 def _pad_flags(lens: np.ndarray, chunk: int = CHUNK) -> np.ndarray:
     """1 where pad_sequence adds a zero row to the document inside its chunk of 10 (main.py:465-467)."""
     flags = np.zeros(len(lens), dtype=np.uint8)
@@ -274,11 +282,10 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
     dev = _device()
     out: Dict[str, ops.ProtocolRanks] = {}
     if m_info["type"] == "colpali":
-        img, t2i, allc = _as_list(img_embeds), _as_list(t2i_txt_embeds), _as_list(all_txt_embeds)
-        n = len(img)
-        i_flat, i_off, i_lens = _flatten(img, dev)
-        t_flat, t_off, t_lens = _flatten(t2i, dev)
-        a_flat, a_off, a_lens = _flatten(allc, dev)
+        n = len(img_embeds)
+        i_flat, i_off, i_lens = _flatten_any(img_embeds, dev)
+        t_flat, t_off, t_lens = _flatten_any(t2i_txt_embeds, dev)
+        a_flat, a_off, a_lens = _flatten_any(all_txt_embeds, dev)
         fl_i, fl_a = _pad_flags(i_lens), _pad_flags(a_lens)
         s_t2i = ops.maxsim_scores(t_flat, t_off, i_flat, i_off, _np_h2d(fl_i, dev, torch.uint8) if fl_i.any() else None)
         s_i2t = ops.maxsim_scores(i_flat, i_off, a_flat, a_off, _np_h2d(fl_a, dev, torch.uint8) if fl_a.any() else None)
