@@ -69,9 +69,26 @@ class ProtocolRanks:
         return {k: 100.0 * c / n for k, c in zip((1, 5, 10), correct)}
 
 
+MAXSIM_WORKSPACE_LIMIT = 16 << 30   # bytes; larger problems are scored in blocks of whole queries
+
+
+def _maxsim_call(q_tok, q_off, nq, d_tok, d_off, nd, d_zero, out) -> None:
+    need = ctypes.c_size_t()
+    h = _lib.lib()
+    _lib.check(h.mmx_maxsim_workspace_bytes(q_tok.shape[0], nd, d_tok.shape[0], ctypes.byref(need)))
+    ws = torch.empty(need.value, dtype=torch.uint8, device=q_tok.device)
+    _lib.check(h.mmx_maxsim_scores(q_tok.data_ptr(), q_off.data_ptr(), nq, q_tok.shape[0], d_tok.data_ptr(),
+                                   d_off.data_ptr(), nd, d_tok.shape[0], q_tok.shape[1] if q_tok.dim() == 2 else 0,
+                                   _ptr(d_zero), out.data_ptr(), out.stride(0), ws.data_ptr(), need.value, _stream()))
+
+
 def maxsim_scores(q_tok: torch.Tensor, q_off: torch.Tensor, d_tok: torch.Tensor, d_off: torch.Tensor,
                   d_zero: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """K2. q_tok [n_qtok,128] / d_tok [n_dtok,128] bf16 CUDA, offsets int32 CUDA -> fp32 [nq, nd] CUDA."""
+    """K2. q_tok [n_qtok,128] / d_tok [n_dtok,128] bf16 CUDA, offsets int32 CUDA -> fp32 [nq, nd] CUDA.
+
+    The kernel's workspace holds one partial sum per (128-row query tile, document) for queries that span several
+    tiles; when that exceeds MAXSIM_WORKSPACE_LIMIT (long queries x many documents: the I2T orientation at scale) the
+    queries are scored in blocks of whole queries (one small device->host read of the offsets)."""
     _need_cuda(q_tok, q_off, d_tok, d_off, d_zero)
     if q_tok.dtype != torch.bfloat16 or d_tok.dtype != torch.bfloat16:
         raise TypeError("MaxSim kernel takes bf16 token embeddings")
@@ -80,12 +97,19 @@ def maxsim_scores(q_tok: torch.Tensor, q_off: torch.Tensor, d_tok: torch.Tensor,
     if out is None:
         out = torch.empty((nq, nd), dtype=torch.float32, device=q_tok.device)
     need = ctypes.c_size_t()
-    h = _lib.lib()
-    _lib.check(h.mmx_maxsim_workspace_bytes(q_tok.shape[0], nd, d_tok.shape[0], ctypes.byref(need)))
-    ws = torch.empty(need.value, dtype=torch.uint8, device=q_tok.device)
-    _lib.check(h.mmx_maxsim_scores(q_tok.data_ptr(), q_off.data_ptr(), nq, q_tok.shape[0], d_tok.data_ptr(),
-                                   d_off.data_ptr(), nd, d_tok.shape[0], q_tok.shape[1] if q_tok.dim() == 2 else 0,
-                                   _ptr(d_zero), out.data_ptr(), out.stride(0), ws.data_ptr(), need.value, _stream()))
+    _lib.check(_lib.lib().mmx_maxsim_workspace_bytes(q_tok.shape[0], nd, d_tok.shape[0], ctypes.byref(need)))
+    if need.value <= MAXSIM_WORKSPACE_LIMIT or nq <= 1:
+        _maxsim_call(q_tok, q_off, nq, d_tok, d_off, nd, d_zero, out)
+        return out
+    off_h = q_off.cpu().numpy().astype(np.int64)
+    rows_per_block = max(128, int(MAXSIM_WORKSPACE_LIMIT // 2 // max(1, nd * 4)) * 128)
+    a = 0
+    while a < nq:
+        b = int(np.searchsorted(off_h, off_h[a] + rows_per_block, side="right")) - 1
+        b = min(nq, max(b, a + 1))
+        sub_off = (q_off[a:b + 1] - q_off[a]).contiguous()
+        _maxsim_call(q_tok[int(off_h[a]):int(off_h[b])], sub_off, b - a, d_tok, d_off, nd, d_zero, out[a:b])
+        a = b
     return out
 
 

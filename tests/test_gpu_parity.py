@@ -108,6 +108,17 @@ def test_maxsim_vs_oracle(mmx_mod, case):
     _assert_close_scores(got, want)
 
 
+def test_maxsim_query_blocking_equals_single_launch(mmx_mod, monkeypatch):
+    """Problems whose carry workspace would exceed the limit are scored in blocks of whole queries: same scores."""
+    docs, queries = synth_colpali(40, 90, doc_len=64, q_len=(1, 300), sigma_q=2.0, seed=21)
+    m_info = {"type": "colpali"}
+    whole = mmx_mod.compute_similarity_scores(docs, queries, m_info, None)
+    monkeypatch.setattr(mmx_mod.ops, "MAXSIM_WORKSPACE_LIMIT", 1 << 16)       # forces blocks of a few hundred rows
+    blocked = mmx_mod.compute_similarity_scores(docs, queries, m_info, None)
+    assert torch.equal(whole, blocked)
+    _assert_close_scores(blocked, oracle.maxsim_scores(queries, docs))
+
+
 def test_maxsim_padded_tensor_input_and_errors(mmx_mod):
     docs, queries = synth_colpali(12, 12, doc_len=40, q_len=(6, 6), seed=3)
     want = oracle.maxsim_scores(queries, docs)
