@@ -399,11 +399,14 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
         values, means = values_d.cpu().numpy(), means_d.cpu().numpy()
         hits, drawn = hits_d.cpu().numpy().astype(np.int64), drawn_d.cpu().numpy()
         alpha = (1 - 0.95) / 2
+        # one vectorised call = the same partition + linear interpolation per row as the reference's two scalar
+        # np.percentile calls per metric (main.py:273-274), with the same (inexact) q values
+        bounds = np.percentile(means, [alpha * 100, (1 - alpha) * 100], axis=1)
         for j, key in enumerate(METRIC_KEYS):                                              # main.py:644-651, :259-278
             v = np.ascontiguousarray(values[:, j])
             aggregated[f"{key}_mean"] = np.mean(v)
-            aggregated[f"{key}_lower"] = np.percentile(means[j], alpha * 100)
-            aggregated[f"{key}_upper"] = np.percentile(means[j], (1 - alpha) * 100)
+            aggregated[f"{key}_lower"] = bounds[0, j]
+            aggregated[f"{key}_upper"] = bounds[1, j]
             aggregated[f"{key}_std"] = np.std(v)
     else:
         ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info)
