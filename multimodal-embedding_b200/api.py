@@ -486,11 +486,14 @@ class FlatMultiVector:
 H2D_DOC_CHUNKS = 8   # host-resident documents are uploaded in this many pieces, each scored while the next one copies
 
 
-def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device) -> torch.Tensor:
+def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device,
+                     flags: Optional[np.ndarray] = None) -> torch.Tensor:
     """K2 over documents that still live in host memory: the upload of document chunk c+1 (copy stream, pinned
-    source) overlaps the scoring of chunk c, so PCIe time hides behind the tensor cores. Returns fp32 [nq, nd]."""
+    source) overlaps the scoring of chunk c, so PCIe time hides behind the tensor cores. Returns fp32 [nq, nd].
+    `flags`: the documents' zero-padding flags when they are not those of this list taken alone (a shard)."""
     nq, nd = len(qv), len(dv)
-    flags = _pad_flags(dv.lens)                       # chunk-of-10 padding flags of the WHOLE list (main.py:465)
+    if flags is None:
+        flags = _pad_flags(dv.lens)                   # chunk-of-10 padding flags of the WHOLE list (main.py:465)
     q_flat, q_off = qv.to_device(dev)
     n_chunks = 1 if dv.flat.is_cuda else max(1, min(H2D_DOC_CHUNKS, nd // 64))
     if n_chunks == 1:
@@ -554,6 +557,13 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     else:
         bounds = [(0, n_local)]
     g_base, n_docs = bounds[rank][0], bounds[-1][1]
+    shard_flags = None
+    if colpali and world > 1:
+        # the reference pads inside chunks of 10 consecutive documents of the WHOLE list (main.py:465): a shard that
+        # does not start on a multiple of 10 needs its neighbours' lengths to know which of its documents get a zero row
+        all_lens: List[Any] = [None] * world
+        dist.all_gather_object(all_lens, np.asarray(dv.lens, dtype=np.int64), group=group)
+        shard_flags = _pad_flags(np.concatenate(all_lens))[g_base:g_base + n_local]
     # ---- the reference's numpy stream (the draws do not depend on the scores). Device mode (K6): one small CTA on a
     # side stream regenerates MT19937 while the embeddings cross PCIe and the scoring kernel runs.
     r = _rng(rng)
@@ -574,7 +584,7 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     # ---- score + threshold pass on this rank's shard (async)
     if colpali:
         ev[0].record()
-        S = _maxsim_streamed(qv, dv, dev)
+        S = _maxsim_streamed(qv, dv, dev, shard_flags)
         ev[1].record()
         local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, threshold_only=True)
     else:
