@@ -28,7 +28,7 @@ namespace shuf {
 
 constexpr int L = 8192;        // words per chunk (accept counts fit uint16)
 constexpr int PB = 64;         // permutations per composition block
-constexpr int MAX_N = 4096;    // work grows with n * |W|; beyond this the host replays the shuffles
+constexpr int MAX_N = 16384;   // work grows with n * |W| (~n^2 P); beyond this the host replays the shuffles
 
 struct Plan {
     long long n_chunks, steps;
@@ -255,6 +255,12 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
     dim3 gt((unsigned)((P + 31) / 32), (unsigned)((n + 31) / 32));
     transpose_kernel<<<gt, 256, 0, stream>>>(arr, n, P, pi);
     const size_t smem = (size_t)n * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_N * 8));
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_N * 8));
+        attr_set = true;
+    }
     compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, nullptr, comp, nullptr);
     compose_scan_kernel<<<1, 512, smem, stream>>>(comp, n, pl.n_blocks, prefix);
     compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, prefix, nullptr, perm);

@@ -452,7 +452,7 @@ def test_device_rng_jump_ahead_starved_budget(mmx_mod):
     assert rs_dev.randint(0, 1 << 30) == rs_ref.randint(0, 1 << 30)
 
 
-@pytest.mark.parametrize("n,n_shuffles", [(2, 9), (3, 40), (5, 300), (64, 120), (600, 300), (2000, 150), (4096, 12)])
+@pytest.mark.parametrize("n,n_shuffles", [(2, 9), (3, 40), (5, 300), (64, 120), (600, 300), (2000, 150), (4096, 12), (10000, 7), (16384, 3)])
 def test_device_shuffle_matches_numpy_cumulative_shuffles(mmx_mod, n, n_shuffles):
     """K6s: the index array after every one of numpy's cumulative in-place shuffles (main.py:296), the number of
     stream words they consumed, and the generator state afterwards — bit for bit."""
@@ -500,7 +500,7 @@ def test_permutation_test_long_arrays_fall_back_to_host_shuffles(mmx_mod, monkey
     rs = np.random.RandomState(3)
     d1, d2 = rs.normal(size=90), rs.normal(0.1, 1.0, size=80)
     p_host = mmx_mod.permutation_test(d1, d2, 300, rng=np.random.RandomState(8))
-    monkeypatch.setattr(mmx_mod.api, "DEVICE_SHUFFLE_MAX_N", 4096)
+    monkeypatch.setattr(mmx_mod.api, "DEVICE_SHUFFLE_MAX_N", 16384)
     p_dev = mmx_mod.permutation_test(d1, d2, 300, rng=np.random.RandomState(8))
     assert p_host == p_dev == oracle.permutation_test(d1, d2, 300, rng=np.random.RandomState(8))
 
