@@ -10,8 +10,11 @@
 // The chain is a finite-state transducer: the state is the current `i` in [1, n-1] (n-1 states), the input one
 // random word; a word is accepted iff (w & mask(i)) <= i, and an accept emits j and moves i -> i-1 (wrapping to n-1:
 // next permutation). That parallelises exactly, with the raw word stream W produced by K6p:
-//   B  tables   for every chunk of L words and EVERY start state, count the accepts (one thread per (chunk, state);
-//               the chunk's words sit in shared memory) — (n-1) * |W| steps of ~9 instructions, all independent;
+//   B  tables   for every chunk of L words and EVERY start state, count the accepts. Runs that start in different
+//               states never cross, and two runs that meet stay together, so the n-1 runs of a chunk coalesce quickly
+//               (n = 2000: 840 distinct runs after 1024 words, 128 after 8192, 40 after 32768): one CTA per chunk keeps
+//               the distinct runs as a sorted array (first start position, state, accepts) in shared memory, advances
+//               them 512 words at a time and compacts equal neighbours in place — ~12x fewer steps than n-1 full runs;
 //   C  chain    one thread walks the chunks: start state and global step offset of each (|W| / L table lookups);
 //   D  emit     one thread per chunk replays it from its now known start state and writes the accepted j values in
 //               step order; the thread that emits the last step reports how many words were consumed;
@@ -26,7 +29,9 @@
 namespace mmx {
 namespace shuf {
 
-constexpr int L = 8192;        // words per chunk (accept counts fit uint16)
+constexpr int L = 32768;       // words per chunk (accept counts fit uint16)
+constexpr int CT = 512;        // threads of a table CTA
+constexpr int RW = 512;        // words per round (simulate, then compact)
 constexpr int PB = 64;         // permutations per composition block
 constexpr int MAX_N = 16384;   // work grows with n * |W| (~n^2 P); beyond this the host replays the shuffles
 
@@ -63,22 +68,89 @@ __device__ __forceinline__ bool step(uint32_t w, int& m, int n1, uint32_t& v) {
     return acc;
 }
 
-// B: accepts[c][m0-1] for every start state m0 of chunk c
-__global__ void __launch_bounds__(256)
+// B: tab[c][pos] = accepts of chunk c when it starts at position pos (state m = n1 - pos), for every pos in [0, n1).
+// The distinct runs live in shared memory as parallel arrays sorted by start position: g = first start position of the
+// run's group, m = current state, a = accepts so far of the group's first member; every member `pos` of the group has
+// accepts (g + a) - pos because merged runs sit at the same unrolled position u = pos + accepts.
+__global__ void __launch_bounds__(CT)
 tables_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, uint16_t* __restrict__ tab) {
-    extern __shared__ uint32_t sw[];
+    extern __shared__ uint32_t sm32[];
+    uint32_t* sw = sm32;                                     // [RW] words of the round
+    uint32_t* su = sm32 + RW;                                // [CT] unrolled positions of a compaction strip
+    uint16_t* sm = reinterpret_cast<uint16_t*>(su + CT);     // [n1] state
+    uint16_t* sa = sm + ((n1 + 1) & ~1);                     // [n1] accepts
+    uint16_t* sg = sa + ((n1 + 1) & ~1);                     // [n1] first start position of the group
+    __shared__ int warp_cnt[CT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long c = blockIdx.x;
-    const long long base = c * L;
-    const int len = (int)min((long long)L, n_words - base);
-    for (int t = threadIdx.x; t < len; t += blockDim.x) sw[t] = words[base + t];
-    __syncthreads();
-    const int m0 = blockIdx.y * blockDim.x + threadIdx.x + 1;
-    if (m0 > n1) return;
-    int m = m0, a = 0;
-    uint32_t v;
+    const long long base_w = c * L;
+    const int len = (int)min((long long)L, n_words - base_w);
+    for (int i = tid; i < n1; i += CT) {
+        sm[i] = (uint16_t)(n1 - i);
+        sa[i] = 0;
+        sg[i] = (uint16_t)i;
+    }
+    int D = n1;
+    for (int r0 = 0; r0 < len; r0 += RW) {
+        const int tl = min(RW, len - r0);
+        __syncthreads();
+        for (int t = tid; t < tl; t += CT) sw[t] = words[base_w + r0 + t];
+        __syncthreads();
+        // ---- advance every distinct run through the round's words
+        for (int i = tid; i < D; i += CT) {
+            int m = sm[i];
+            uint32_t acc = sa[i], v;
 #pragma unroll 4
-    for (int t = 0; t < len; ++t) a += step(sw[t], m, n1, v) ? 1 : 0;
-    tab[c * n1 + (m0 - 1)] = (uint16_t)a;
+            for (int t = 0; t < tl; ++t) acc += step(sw[t], m, n1, v) ? 1u : 0u;
+            sm[i] = (uint16_t)m;
+            sa[i] = (uint16_t)acc;
+        }
+        __syncthreads();
+        if (D == 1) continue;
+        // ---- compact in place: neighbours at the same unrolled position have merged for good
+        int out = 0;
+        uint32_t prev_u = 0xffffffffu;
+        for (int s0 = 0; s0 < D; s0 += CT) {
+            const int i = s0 + tid;
+            const bool valid = i < D;
+            const uint32_t mm = valid ? sm[i] : 0u, aa = valid ? sa[i] : 0u, gg = valid ? sg[i] : 0u;
+            const uint32_t u = gg + aa;
+            su[tid] = u;
+            __syncthreads();
+            const uint32_t before = tid > 0 ? su[tid - 1] : prev_u;
+            const uint32_t strip_last = su[min(CT, D - s0) - 1];
+            const bool head = valid && u != before;
+            const unsigned bal = __ballot_sync(0xffffffffu, head);
+            if (lane == 0) warp_cnt[warp] = __popc(bal);
+            __syncthreads();
+            int off = __popc(bal & ((1u << lane) - 1u)), total = 0;
+#pragma unroll
+            for (int w = 0; w < CT / 32; ++w) {
+                const int cw = warp_cnt[w];
+                if (w < warp) off += cw;
+                total += cw;
+            }
+            if (head) {  // new index <= old index, and every element of this strip has been read
+                sm[out + off] = (uint16_t)mm;
+                sa[out + off] = (uint16_t)aa;
+                sg[out + off] = (uint16_t)gg;
+            }
+            out += total;
+            prev_u = strip_last;
+            __syncthreads();
+        }
+        D = out;
+    }
+    __syncthreads();
+    // ---- expand: every start position takes its group's unrolled end position
+    for (int pos = tid; pos < n1; pos += CT) {
+        int lo = 0, hi = D;  // largest group with sg <= pos
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)sg[mid] <= pos) lo = mid; else hi = mid;
+        }
+        tab[c * n1 + pos] = (uint16_t)((int)sg[lo] + (int)sa[lo] - pos);
+    }
 }
 
 // C: start state / step offset of every chunk; end_chunk = the chunk in which the last step falls (-1: too few words)
@@ -91,7 +163,7 @@ __global__ void chain_kernel(const uint16_t* __restrict__ tab, long long n_chunk
     for (long long c = 0; c < n_chunks; ++c) {
         start_m[c] = m;
         start_s[c] = s;
-        const int a = tab[c * n1 + (m - 1)];
+        const int a = tab[c * n1 + (n1 - m)];
         s += a;
         if (s >= steps) {
             end_chunk = c;
@@ -105,12 +177,17 @@ __global__ void chain_kernel(const uint16_t* __restrict__ tab, long long n_chunk
     info[1] = -1;  // words consumed, written by the emit kernel
 }
 
-// D: replay every chunk from its start state and write the accepted values in step order
-__global__ void __launch_bounds__(64)
+// D: replay every chunk from its start state and write the accepted values in step order. One warp per chunk: the
+// run itself is one dependent chain (lane 0), the other lanes stage the chunk's words in shared memory tile by tile so
+// that the chain never waits for global memory.
+constexpr int ET = 1024;  // words per staged tile
+__global__ void __launch_bounds__(32)
 emit_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, long long steps,
             const int32_t* __restrict__ start_m, const long long* __restrict__ start_s, long long* __restrict__ info,
             int32_t* __restrict__ jout) {
-    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t sw[2][ET];
+    const long long c = blockIdx.x;
+    const int lane = threadIdx.x;
     const long long end_chunk = info[0];
     if (end_chunk < 0 || c > end_chunk) return;
     const long long base = c * L;
@@ -118,14 +195,28 @@ emit_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, long 
     int m = start_m[c];
     long long s = start_s[c];
     uint32_t v;
-    for (int t = 0; t < len; ++t) {
-        if (step(__ldg(words + base + t), m, n1, v)) {
-            jout[s] = (int32_t)v;
-            if (++s == steps) {
-                info[1] = base + t + 1;  // exactly this many words were consumed
-                return;
+    bool done = false;
+    for (int t = lane; t < min(ET, len); t += 32) sw[0][t] = words[base + t];
+    __syncwarp();
+    for (int t0 = 0, buf = 0; t0 < len && !done; t0 += ET, buf ^= 1) {
+        const int tl = min(ET, len - t0);
+        if (lane > 0) {  // 31 lanes fetch the next tile while lane 0 walks this one
+            const int nl = min(ET, len - (t0 + ET));
+            for (int t = lane - 1; t < nl; t += 31) sw[buf ^ 1][t] = words[base + t0 + ET + t];
+        } else {
+            for (int t = 0; t < tl; ++t) {
+                if (step(sw[buf][t], m, n1, v)) {
+                    jout[s] = (int32_t)v;
+                    if (++s == steps) {
+                        info[1] = base + t0 + t + 1;  // exactly this many words were consumed
+                        done = true;
+                        break;
+                    }
+                }
             }
         }
+        done = __shfl_sync(0xffffffffu, done, 0);
+        __syncwarp();
     }
 }
 
@@ -240,12 +331,18 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
     int32_t* comp = reinterpret_cast<int32_t*>(ws + pl.off_c - 256);
     int32_t* prefix = reinterpret_cast<int32_t*>(ws + pl.off_d - 256);
     const int n1 = n - 1;
-    dim3 gb((unsigned)pl.n_chunks, (unsigned)((n1 + 255) / 256));
-    tables_kernel<<<gb, 256, L * 4, stream>>>(words, n_words, n1, tab);
+    const size_t smem_tab = (size_t)(RW + CT) * 4 + 3 * (size_t)((n1 + 1) & ~1) * 2;
+    static bool tab_attr = false;
+    if (!tab_attr) {
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (RW + CT) * 4 + 3 * MAX_N * 2));
+        tab_attr = true;
+    }
+    tables_kernel<<<(unsigned)pl.n_chunks, CT, smem_tab, stream>>>(words, n_words, n1, tab);
     MMX_CHECK_CUDA(cudaGetLastError());
     chain_kernel<<<1, 32, 0, stream>>>(tab, pl.n_chunks, n1, pl.steps, start_m, start_s,
                                        reinterpret_cast<long long*>(info));
-    emit_kernel<<<(unsigned)((pl.n_chunks + 63) / 64), 64, 0, stream>>>(words, n_words, n1, pl.steps, start_m, start_s,
+    emit_kernel<<<(unsigned)pl.n_chunks, 32, 0, stream>>>(words, n_words, n1, pl.steps, start_m, start_s,
                                                                        reinterpret_cast<long long*>(info), jout);
     MMX_CHECK_CUDA(cudaGetLastError());
     // when the words did not suffice (info[1] = -1) the swaps are skipped and the stages below shuffle unspecified
