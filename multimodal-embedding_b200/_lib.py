@@ -122,6 +122,7 @@ _SIGNATURES = {
     ]),
     "mmx_mt19937_randint": (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p, _c.c_void_p]),
     "mmx_mt19937_par_scratch_bytes": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_size_t)]),
+    "mmx_mt19937_par_set_bit_positions": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int]),
     "mmx_mt19937_par_set_slack": (_c.c_int, [_c.c_double, _c.c_double]),
     "mmx_mt19937_randint_par": (_c.c_int, [
         _c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p,            # state, high, count, out

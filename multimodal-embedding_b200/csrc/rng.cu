@@ -175,10 +175,14 @@ namespace rng {
 constexpr int PTHREADS = 256;
 constexpr int PWARPS = PTHREADS / 32;
 constexpr int XBLOCKS = 33;  // 33 * 624 = 20592 >= 19937 + 623 raw words feed the convolution
+constexpr int XPAD = 768;    // zero words behind the stream: the target of padded bit positions (index XBLOCKS * 624)
 
 struct ParParams {
     const uint32_t* state;        // [625] key + pos (read only)
     const uint32_t* polys;        // [n_poly][624] jump polynomials, polys[k-1] = x^(k*seg_words) mod phi
+    const uint16_t* bitpos;       // nullable [n_poly][bitpos_ld]: positions of the set bits of every polynomial, padded
+    const int32_t* bitcnt;        //   with a position whose x word is zero (see mt_par_expand_kernel); bitcnt[k] = count
+    int bitpos_ld;
     uint32_t* xstream;            // [XBLOCKS * 624] raw words that follow the current key (key itself = block 0)
     uint32_t* seg_states;         // [n_seg][624]
     unsigned long long* seg_cnt;  // [n_seg]
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(PTHREADS)
 mt_par_count_kernel(const ParParams p) {
     extern __shared__ uint32_t sm[];
     uint32_t* x = sm;                   // [XBLOCKS * N] raw stream from the base key (segments k > 0)
-    uint32_t* key0 = sm + XBLOCKS * N;  // two block buffers for the segment itself
+    uint32_t* key0 = sm + XBLOCKS * N + XPAD;  // two block buffers for the segment itself
     uint32_t* key1 = key0 + N;
     __shared__ unsigned long long wcnt[PWARPS];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -231,13 +235,26 @@ mt_par_count_kernel(const ParParams p) {
         for (int i = t; i < N; i += PTHREADS) key0[i] = p.state[i];
     } else {
         for (int i = t; i < XBLOCKS * N; i += PTHREADS) x[i] = p.xstream[i];
+        for (int i = t; i < XPAD; i += PTHREADS) x[XBLOCKS * N + i] = 0u;
         __syncthreads();
-        const uint32_t* g = p.polys + (size_t)(k - 1) * N;
         uint32_t a0 = 0, a1 = 0, a2 = 0;
         const bool third = t + 512 < N;
         const uint32_t* xt = x + t;
+        if (p.bitpos != nullptr) {
+            // precomputed set-bit positions: four independent gathers in flight, no bit scanning in the loop
+            const uint16_t* bp = p.bitpos + (size_t)(k - 1) * p.bitpos_ld;
+            const int nb = (__ldg(p.bitcnt + (k - 1)) + 3) & ~3;   // the padding positions index zero words
+            for (int j = 0; j < nb; j += 4) {
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(bp + j));
+                const int i0 = q.x & 0xffff, i1 = q.x >> 16, i2 = q.y & 0xffff, i3 = q.y >> 16;
+                a0 ^= xt[i0] ^ xt[i1] ^ xt[i2] ^ xt[i3];
+                a1 ^= xt[i0 + 256] ^ xt[i1 + 256] ^ xt[i2 + 256] ^ xt[i3 + 256];
+                if (third) a2 ^= xt[i0 + 512] ^ xt[i1 + 512] ^ xt[i2 + 512] ^ xt[i3 + 512];
+            }
+        }
+        const uint32_t* g = p.polys + (size_t)(k - 1) * N;
         uint32_t gnext = __ldg(g);
-        for (int w = 0; w < N; ++w) {
+        for (int w = 0; w < (p.bitpos != nullptr ? 0 : N); ++w) {
             uint32_t gw = gnext;
             if (w + 1 < N) gnext = __ldg(g + w + 1);
             const uint32_t* xw = xt + w * 32;
@@ -418,6 +435,24 @@ extern "C" int mmx_mt19937_par_scratch_bytes(int n_poly, size_t* bytes) {
     return 0;
 }
 
+// Optional accelerator of the jump convolution: the set-bit positions of every polynomial of the table the caller
+// passes as `polys` (uint16 [n_poly][ld], rows padded to a multiple of 4 with the value 33 * 624 = 20592) and their
+// counts. Registered once per process by the binding; results do not depend on it.
+static const uint16_t* g_bitpos = nullptr;
+static const int32_t* g_bitcnt = nullptr;
+static const uint32_t* g_bitpos_polys = nullptr;
+static int g_bitpos_ld = 0;
+extern "C" int mmx_mt19937_par_set_bit_positions(const uint32_t* polys, const uint16_t* bitpos, const int32_t* bitcnt,
+                                                 int ld) {
+    MMX_REQUIRE((bitpos == nullptr) == (bitcnt == nullptr) && (bitpos == nullptr || (ld >= 4 && ld % 4 == 0)),
+                "bad bit-position table");
+    g_bitpos_polys = polys;
+    g_bitpos = bitpos;
+    g_bitcnt = bitcnt;
+    g_bitpos_ld = ld;
+    return 0;
+}
+
 // rng_incl = inclusive maximum of the masked-rejection draw (0xffffffff: every raw word is a value)
 static int par_generate(uint32_t* state, uint32_t rng_incl, int64_t count, int32_t* out, const uint32_t* polys,
                         int n_poly, int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
@@ -437,9 +472,13 @@ static int par_generate(uint32_t* state, uint32_t rng_incl, int64_t count, int32
     p.state = state;
     p.polys = polys;
     p.seg_blocks = seg_blocks;
+    const bool fast = g_bitpos != nullptr && g_bitpos_polys == polys;
+    p.bitpos = fast ? g_bitpos : nullptr;
+    p.bitcnt = fast ? g_bitcnt : nullptr;
+    p.bitpos_ld = fast ? g_bitpos_ld : 0;
     p.rng = rng_incl;
     p.mask = mask_of(p.rng);
-    const size_t smem = (size_t)(XBLOCKS + 2) * N * 4;
+    const size_t smem = ((size_t)(XBLOCKS + 2) * N + XPAD) * 4;
     MMX_CHECK_CUDA(cudaFuncSetAttribute(mt_par_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const double per_seg = (double)seg_blocks * N;
     // values one launch (n_poly + 1 segments) is budgeted to deliver; larger requests are chained launches, each

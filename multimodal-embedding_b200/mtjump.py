@@ -152,3 +152,18 @@ def jump_key(key: np.ndarray, g_words: np.ndarray) -> np.ndarray:
     for i in np.nonzero(bits)[0]:
         out ^= x[i:i + N]
     return out
+
+
+PAD_POSITION = 33 * N     # index of a zero word behind the 33-block stream the device convolves (csrc/rng.cu XPAD)
+
+
+def bit_positions(table: np.ndarray):
+    """Set-bit positions of every polynomial: (uint16 [n_poly, ld] padded with PAD_POSITION, ld % 4 == 0; int32 counts)."""
+    bits = np.unpackbits(np.ascontiguousarray(table).view(np.uint8), axis=1, bitorder="little")
+    cnt = bits.sum(axis=1).astype(np.int32)
+    ld = (int(cnt.max()) + 3) & ~3
+    pos = np.full((table.shape[0], ld), PAD_POSITION, dtype=np.uint16)
+    for k in range(table.shape[0]):
+        idx = np.nonzero(bits[k])[0]
+        pos[k, : len(idx)] = idx
+    return pos, cnt

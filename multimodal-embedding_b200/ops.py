@@ -339,10 +339,18 @@ class DeviceRng:
         dev = self.state.device
         if dev not in DeviceRng._tables:
             from . import mtjump
-            polys = torch.from_numpy(mtjump.load_table(build_if_missing=False).view(np.int32)).to(dev)
+            table = mtjump.load_table(build_if_missing=False)
+            polys = torch.from_numpy(table.view(np.int32)).to(dev)
             need = ctypes.c_size_t()
             _lib.check(_lib.lib().mmx_mt19937_par_scratch_bytes(mtjump.N_POLY, ctypes.byref(need)))
-            DeviceRng._tables[dev] = (polys, torch.empty(need.value, dtype=torch.uint8, device=dev))
+            # set-bit positions of every polynomial (the jump convolution gathers x[n + i] over them)
+            pos, cnt = mtjump.bit_positions(table)
+            pos_d = torch.from_numpy(pos.view(np.int16)).to(dev)
+            cnt_d = torch.from_numpy(cnt).to(dev)
+            if len(DeviceRng._tables) == 0:            # the library keeps ONE registration (the first device's)
+                _lib.check(_lib.lib().mmx_mt19937_par_set_bit_positions(polys.data_ptr(), pos_d.data_ptr(),
+                                                                        cnt_d.data_ptr(), pos.shape[1]))
+            DeviceRng._tables[dev] = (polys, torch.empty(need.value, dtype=torch.uint8, device=dev), pos_d, cnt_d)
         return DeviceRng._tables[dev]
 
     def randint(self, high: int, count: int, parallel: Optional[bool] = None) -> torch.Tensor:
@@ -353,7 +361,7 @@ class DeviceRng:
             parallel = count >= self.PAR_MIN_COUNT
         if parallel:
             from . import mtjump
-            polys, scratch = self._par_buffers()
+            polys, scratch = self._par_buffers()[:2]
             _lib.check(_lib.lib().mmx_mt19937_randint_par(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
                                                           polys.data_ptr(), mtjump.N_POLY, mtjump.SEG_BLOCKS,
                                                           scratch.data_ptr(), scratch.numel(), _stream()))
@@ -366,7 +374,7 @@ class DeviceRng:
         """The next `count` raw 32-bit outputs (as int32 bit patterns). advance=False leaves the generator where it
         is (the draws are made from a copy of the state); ``skip`` then moves it by the number actually consumed."""
         from . import mtjump
-        polys, scratch = self._par_buffers()
+        polys, scratch = self._par_buffers()[:2]
         st = self.state if advance else self.state.clone()
         out = torch.empty((count,), dtype=torch.int32, device=self.state.device)
         _lib.check(_lib.lib().mmx_mt19937_raw_par(st.data_ptr(), int(count), out.data_ptr(), polys.data_ptr(),
@@ -377,7 +385,7 @@ class DeviceRng:
     def skip(self, count: int) -> None:
         """Advance the generator by `count` raw words without materialising them."""
         from . import mtjump
-        polys, scratch = self._par_buffers()
+        polys, scratch = self._par_buffers()[:2]
         _lib.check(_lib.lib().mmx_mt19937_raw_par(self.state.data_ptr(), int(count), None, polys.data_ptr(),
                                                   mtjump.N_POLY, mtjump.SEG_BLOCKS, scratch.data_ptr(),
                                                   scratch.numel(), _stream()))
