@@ -271,13 +271,15 @@ def permutation_test(data1: np.ndarray, data2: np.ndarray, n_permutations: int =
 
 # ------------------------------------------------------------------------------------------------ fused path
 def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, caps_per_img: int = 5,
-                   want_bits: bool = True, want_top10: bool = False) -> Dict[str, ops.ProtocolRanks]:
+                   want_bits: bool = True, want_top10: bool = False, want_ties: bool = False) -> Dict[str, ops.ProtocolRanks]:
     """One scoring pass over the BASE embeddings for the three protocols of run_bootstrap_benchmark
     (main.py:599-624 GT structure: query i <-> image i, image i <-> captions [5i, 5i+5)).
 
     Dense models never materialise a score matrix (K1). ColPali writes the final [n_q, n_doc] fp32 scores (one float
     per 5.3 MFLOP pair) and ranks them with KR; I2T uses images as MaxSim queries (v28 :375-386) and I2T_Sym the
-    transposed T2I matrix exactly as main.py:624. ``want_top10`` also fills ``top_s`` / ``top_i`` of every protocol with
+    transposed T2I matrix exactly as main.py:624. ``want_ties`` fills ``ties`` with the tie report of SURVEY 8a (T2):
+    per query, the non-ground-truth columns that score exactly the threshold (``ops.tie_summary`` counts the queries
+    whose Recall@k depends on torch.topk's unspecified order among them). ``want_top10`` also fills ``top_s`` / ``top_i`` of every protocol with
     the retrieved items (`torch.topk(row, 10)` of main.py:333,362,372) — still without a dense score matrix."""
     dev = _device()
     out: Dict[str, ops.ProtocolRanks] = {}
@@ -298,6 +300,10 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
         if want_top10:
             for name, sc in (("T2I", s_t2i), ("I2T", s_i2t), ("I2T_Sym", s_sym)):
                 out[name].top_s, out[name].top_i = ops.topk_from_scores(sc, 10)
+        if want_ties:
+            for name, sc, (go, gi) in (("T2I", s_t2i, (id_off, id_idx)), ("I2T", s_i2t, (b_off, b_idx)),
+                                       ("I2T_Sym", s_sym, (id_off, id_idx))):
+                out[name].ties = ops.exact_tie_counts(out[name], go, gi, scores=sc)
     else:
         img = _h2d(_as_bf16(img_embeds, "img_embeds"), dev)
         t2i = _h2d(_as_bf16(t2i_txt_embeds, "t2i_txt_embeds"), dev)
@@ -311,6 +317,10 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
         if want_top10:
             for name, (qq, gg) in (("T2I", (t2i, img)), ("I2T", (img, allc)), ("I2T_Sym", (img, t2i))):
                 out[name].top_s, out[name].top_i = ops.dense_topk(qq, gg, 10)
+        if want_ties:
+            for name, (qq, gg), (go, gi) in (("T2I", (t2i, img), (id_off, id_idx)), ("I2T", (img, allc), (b_off, b_idx)),
+                                             ("I2T_Sym", (img, t2i), (id_off, id_idx))):
+                out[name].ties = ops.exact_tie_counts(out[name], go, gi, Q=qq, G=gg)
     out["I2T"].col2unit = torch.arange(n * caps_per_img, dtype=torch.int32, device=dev) // caps_per_img
     return out
 
@@ -359,11 +369,12 @@ def _bootstrap_counts_device(ranks: Dict[str, ops.ProtocolRanks], sample_indices
 
 def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, n_iterations: int,
                                   rng=None, t2i_captions: Optional[List[str]] = None, encoding_time: float = 0.0,
-                                  t_start: Optional[float] = None) -> Dict[str, Any]:
+                                  t_start: Optional[float] = None, tie_report: bool = False) -> Dict[str, Any]:
     """Everything run_bootstrap_benchmark does after encoding (main.py:563-667) -> the 42-column row dict.
 
     numpy stream consumption matches the reference: n_iterations x choice(N, N), then for each of the nine metric
-    keys in insertion order 10 000 x choice(values, n_iterations)."""
+    keys in insertion order 10 000 x choice(values, n_iterations). ``tie_report`` adds ``_tie_report``: per protocol, how
+    many base queries have non-ground-truth columns tied bit for bit with their threshold (tie class T2)."""
     t0 = time.time() if t_start is None else t_start
     n_images = len(img_embeds)
     aggregated: Dict[str, Any] = {"Model": m_info["name"]}
@@ -384,7 +395,7 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
                 len(METRIC_KEYS), N_BOOTSTRAP, n_iterations)                                            # main.py:269
             rng_done = torch.cuda.Event()
             rng_done.record(side)
-        ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info)
+        ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info, want_ties=tie_report)
         main.wait_event(rng_done)
         for t in (sample_indices, ci_idx):
             t.record_stream(main)
@@ -409,7 +420,7 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
             aggregated[f"{key}_upper"] = bounds[1, j]
             aggregated[f"{key}_std"] = np.std(v)
     else:
-        ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info)
+        ranks = score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info, want_ties=tie_report)
         sample_indices = _rng(rng).randint(0, n_images, size=(n_iterations, n_images))
         correct, hits, drawn = bootstrap_from_ranks(ranks, sample_indices, n_images, want_hits=True)
         values = 100.0 * correct / n_images                                                # main.py:358,368,378
@@ -433,6 +444,8 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     aggregated["_failure_analysis"] = aggregate_failure_from_hits(caps, hits, drawn)      # main.py:664
     aggregated["_bootstrap_values"] = {k: values[:, j].copy() for j, k in enumerate(METRIC_KEYS)}
     aggregated["_base_metrics"] = base_metrics(ranks)
+    if tie_report:
+        aggregated["_tie_report"] = {name: ops.tie_summary(ranks[name]) for name in ("T2I", "I2T", "I2T_Sym")}
     return aggregated
 
 

@@ -53,6 +53,7 @@ class ProtocolRanks:
     col2unit: Optional[torch.Tensor] = None
     q_unit: Optional[torch.Tensor] = None
     scores: Optional[torch.Tensor] = None
+    ties: Optional[torch.Tensor] = None       # [nq] int32 non-GT columns scoring EXACTLY the threshold (tie class T2)
     top_s: Optional[torch.Tensor] = None      # [nq, k] fp32 top-k scores (KT), higher first, ties by lower column
     top_i: Optional[torch.Tensor] = None      # [nq, k] int32 global column ids, -1 = padding
 
@@ -189,6 +190,52 @@ def rank_from_scores(scores: torch.Tensor, gt_off: torch.Tensor, gt_idx: torch.T
         _lib.check(h.mmx_rank_from_scores(scores.data_ptr(), nq, ng, ld, gt_off.data_ptr(), gt_idx.data_ptr(), g_base,
                                           MODE_COUNT, thr.data_ptr(), cnt.data_ptr(), _ptr(bits), wpr, _stream()))
     return ProtocolRanks(thr=thr, cnt_above=cnt, bits=bits, n_cols=ng)
+
+
+def _just_below(thr: torch.Tensor) -> torch.Tensor:
+    """The largest float below each threshold: `S > just_below(t)` is `S >= t` (-inf stays -inf)."""
+    return torch.nextafter(thr, torch.full_like(thr, float("-inf")))
+
+
+def _gt_slices(gt_off: torch.Tensor, gt_idx: torch.Tensor):
+    """The c-th ground-truth column of every query as single-column CSR pairs (queries with fewer columns repeat
+    their last one; queries without any are skipped by the kernels)."""
+    sizes = (gt_off[1:] - gt_off[:-1]).long()
+    nq = sizes.numel()
+    for c in range(int(sizes.max().item()) if nq else 0):
+        has = sizes > 0
+        pos = gt_off[:-1].long() + torch.minimum(torch.full_like(sizes, c), (sizes - 1).clamp_min(0))
+        idx_c = torch.where(has, gt_idx[pos.clamp_max(max(gt_idx.numel() - 1, 0))].long(), torch.zeros_like(pos)).to(torch.int32)
+        off_c = torch.cat([torch.zeros(1, dtype=torch.int64, device=sizes.device), has.long().cumsum(0)]).to(torch.int32)
+        yield c, sizes, off_c, idx_c[has].contiguous()
+
+
+def exact_tie_counts(r: ProtocolRanks, gt_off: torch.Tensor, gt_idx: torch.Tensor, *, Q: Optional[torch.Tensor] = None,
+                     G: Optional[torch.Tensor] = None, scores: Optional[torch.Tensor] = None, g_base: int = 0) -> torch.Tensor:
+    """Tie report (tie class T2): for every query the number of NON-ground-truth columns whose score equals
+    the ground-truth threshold bit for bit — the only place where `gt in torch.topk(row, k)` (main.py:333) depends on
+    torch's unspecified order of tied scores. Uses the ranking kernels only: one more COUNT pass with the bar just
+    below the threshold gives #{S >= thr}; one THRESHOLD pass per ground-truth slot gives every GT column's own score
+    (same MMA path, bit-identical), hence how many GT columns sit exactly at the threshold.
+    Pass (Q, G) for the dense path (K1) or `scores` for a materialised matrix (KR)."""
+    ge = (dense_rank(Q, G, gt_off, gt_idx, want_bits=False, g_base=g_base, thr=_just_below(r.thr)) if scores is None
+          else rank_from_scores(scores, gt_off, gt_idx, want_bits=False, g_base=g_base, thr=_just_below(r.thr)))
+    n_gt_at_thr = torch.zeros_like(r.cnt_above)
+    for c, sizes, off_c, idx_c in _gt_slices(gt_off, gt_idx):
+        one = (dense_rank(Q, G, off_c, idx_c, g_base=g_base, threshold_only=True) if scores is None
+               else rank_from_scores(scores, off_c, idx_c, g_base=g_base, threshold_only=True))
+        n_gt_at_thr += ((one.thr == r.thr) & (sizes > c)).to(torch.int32)
+    return ge.cnt_above - r.cnt_above - n_gt_at_thr
+
+
+def tie_summary(r: ProtocolRanks) -> dict:
+    """Queries whose Recall@k could flip with the order of exactly tied scores: cnt_above < k <= cnt_above + ties."""
+    if r.ties is None:
+        raise ValueError("no tie counts (score_and_rank(..., want_ties=True))")
+    out = {"queries_with_exact_ties": int((r.ties > 0).sum().item())}
+    for k in (1, 5, 10):
+        out[f"R@{k}_depends_on_tie_order"] = int(((r.cnt_above < k) & (r.cnt_above + r.ties >= k)).sum().item())
+    return out
 
 
 def topk_from_scores(scores: torch.Tensor, k: int = 10, g_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -259,6 +259,39 @@ def test_dense_arbitrary_gt_and_sharded_gallery(mmx_mod):
     assert torch.equal(torch.cat(cols, dim=1), full.bits)
 
 
+def test_tie_report_counts_exact_ties_only(mmx_mod):
+    """Tie class T2: duplicated gallery rows tie bit for bit with the ground truth; the report counts exactly those
+    (dense path without a matrix, and the same through KR on the materialised scores), GT duplicates (T4) excluded."""
+    dev = _dev()
+    n, dim = 300, 128
+    img, all_txt = synth_dense(n, dim, 2.0, seed=21)
+    img = img.clone()
+    img[10] = img[3]                  # image 10 is a copy of image 3: T2I queries 3 and 10 tie between the two columns
+    img[77] = img[3]
+    all_txt = all_txt.clone()
+    all_txt[26] = all_txt[25]         # two identical GT captions of image 5 (T4): not a non-GT tie
+    t2i = all_txt[0::5].contiguous()
+    r = mmx_mod.score_and_rank(img, t2i, all_txt, {"type": "dense", "name": "t"}, want_ties=True)
+    S = mmx_mod.ops.dense_scores(t2i.to(dev), img.to(dev)).cpu()
+    thr = S.diagonal()
+    want = ((S == thr[:, None]).sum(1) - 1).int()
+    assert torch.equal(r["T2I"].ties.cpu(), want) and int(want[3]) == 2 and int(want[10]) >= 1
+    S_i2t = mmx_mod.ops.dense_scores(img.to(dev), all_txt.to(dev)).cpu()
+    thr_i = torch.stack([S_i2t[i, 5 * i:5 * i + 5].max() for i in range(n)])
+    non_gt = torch.ones_like(S_i2t, dtype=torch.bool)
+    for i in range(n):
+        non_gt[i, 5 * i:5 * i + 5] = False
+    want_i = ((S_i2t == thr_i[:, None]) & non_gt).sum(1).int()
+    assert torch.equal(r["I2T"].ties.cpu(), want_i)
+    summ = mmx_mod.ops.tie_summary(r["T2I"])
+    assert summ["queries_with_exact_ties"] == int((want > 0).sum()) and summ["R@1_depends_on_tie_order"] >= 1
+    # KR on the materialised matrix gives the same report
+    off, idx = mmx_mod.ops.csr_from_sets([[i] for i in range(n)])
+    off_d, idx_d = torch.from_numpy(off).to(dev), torch.from_numpy(idx).to(dev)
+    rk = mmx_mod.ops.rank_from_scores(S.to(dev), off_d, idx_d)
+    assert torch.equal(mmx_mod.ops.exact_tie_counts(rk, off_d, idx_d, scores=S.to(dev)).cpu(), want)
+
+
 # ----------------------------------------------------------------------------------------------- metrics (KR)
 def test_compute_metrics_detailed_golden(mmx_mod, golden_dir):
     z = np.load(golden_dir / "dense.npz")
