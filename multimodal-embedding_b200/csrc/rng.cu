@@ -251,19 +251,21 @@ mt_par_count_kernel(const ParParams p) {
                 a1 ^= xt[i0 + 256] ^ xt[i1 + 256] ^ xt[i2 + 256] ^ xt[i3 + 256];
                 if (third) a2 ^= xt[i0 + 512] ^ xt[i1 + 512] ^ xt[i2 + 512] ^ xt[i3 + 512];
             }
-        }
-        const uint32_t* g = p.polys + (size_t)(k - 1) * N;
-        uint32_t gnext = __ldg(g);
-        for (int w = 0; w < (p.bitpos != nullptr ? 0 : N); ++w) {
-            uint32_t gw = gnext;
-            if (w + 1 < N) gnext = __ldg(g + w + 1);
-            const uint32_t* xw = xt + w * 32;
-            while (gw) {
-                const int i = __ffs(gw) - 1;
-                gw &= gw - 1;
-                a0 ^= xw[i];
-                a1 ^= xw[i + 256];
-                if (third) a2 ^= xw[i + 512];
+        } else {
+            // no position table registered: scan the bits of the polynomial word by word
+            const uint32_t* g = p.polys + (size_t)(k - 1) * N;
+            uint32_t gnext = __ldg(g);
+            for (int w = 0; w < N; ++w) {
+                uint32_t gw = gnext;
+                if (w + 1 < N) gnext = __ldg(g + w + 1);
+                const uint32_t* xw = xt + w * 32;
+                while (gw) {
+                    const int i = __ffs(gw) - 1;
+                    gw &= gw - 1;
+                    a0 ^= xw[i];
+                    a1 ^= xw[i + 256];
+                    if (third) a2 ^= xw[i + 512];
+                }
             }
         }
         key0[t] = a0;

@@ -538,6 +538,24 @@ def test_permutation_test_long_arrays_fall_back_to_host_shuffles(mmx_mod, monkey
     assert p_host == p_dev == oracle.permutation_test(d1, d2, 300, rng=np.random.RandomState(8))
 
 
+def test_device_rng_jump_ahead_without_position_table(mmx_mod):
+    """The registered set-bit-position table only accelerates the jump convolution: with it unregistered the bit-scanning
+    path gives the same stream."""
+    h = mmx_mod._lib.lib()
+    d = mmx_mod.ops.DeviceRng(np.random.RandomState(11))
+    polys, _, pos_d, cnt_d = d._par_buffers()
+    try:
+        mmx_mod._lib.check(h.mmx_mt19937_par_set_bit_positions(None, None, None, 0))
+        got = d.randint(5000, 3_000_000, parallel=True).cpu().numpy()
+    finally:
+        mmx_mod._lib.check(h.mmx_mt19937_par_set_bit_positions(polys.data_ptr(), pos_d.data_ptr(), cnt_d.data_ptr(),
+                                                               pos_d.shape[1]))
+    again = d.randint(5000, 1_000_000, parallel=True).cpu().numpy()
+    rs = np.random.RandomState(11)
+    assert np.array_equal(got.astype(np.int64), rs.randint(0, 5000, size=3_000_000))
+    assert np.array_equal(again.astype(np.int64), rs.randint(0, 5000, size=1_000_000))
+
+
 def test_device_rng_global_stream_and_host_mode_agree(mmx_mod, golden_dir, monkeypatch):
     """bootstrap_confidence_interval on the GLOBAL np.random stream: device-drawn (default) and host-drawn index
     streams give the same tuple and leave np.random in the same state as the reference's 10 000 choice() calls."""
