@@ -10,7 +10,7 @@ Both fall out of the strict-greater counts the ranking kernels already produce:
 """
 from __future__ import annotations
 
-from typing import Any, Dict, List, Optional, Sequence, Union
+from typing import Any, Dict, List, Optional, Union
 
 import numpy as np
 import torch

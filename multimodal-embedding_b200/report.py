@@ -16,7 +16,7 @@ from typing import Any, Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
 
-from .api import METRIC_KEYS, permutation_test
+from .api import permutation_test
 
 BootstrapData = Dict[str, Dict[str, np.ndarray]]       # model -> metric key -> per-iteration values
 

@@ -13,7 +13,7 @@ work on any torch.distributed backend (nccl on the B200s, gloo in the CPU tests)
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+from typing import List, Tuple
 
 import torch
 import torch.distributed as dist

@@ -9,7 +9,7 @@ two against each other and against the golden vectors produced by the reference'
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Dict, List, Optional, Sequence
+from typing import Any, Callable, Dict, List, Optional
 
 import numpy as np
 import torch

@@ -9,7 +9,7 @@ The reference draws from the GLOBAL numpy stream; every function takes an option
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 
