@@ -1,5 +1,5 @@
 """Gallery/document sharding across the GPUs of one box: one process per GPU, queries replicated,
-gallery columns split into contiguous shards, exactly two tiny collectives per scoring pass:
+gallery columns split into contiguous balanced shards, exactly two tiny collectives per scoring pass:
 
   1. all-reduce(MAX) of the per-query GT thresholds (the GT column of a query lives on one shard only);
   2. all-reduce(SUM) of the strict-greater counts + all-gather of each shard's bitmask columns.
@@ -20,11 +20,20 @@ import torch.distributed as dist
 
 from .ops import ProtocolRanks
 
-SHARD_ALIGN = 32   # shard boundaries fall on bitmask word boundaries
+SHARD_ALIGN = 1    # shards are balanced to one column; merge_ranks shifts the bit columns into place
 
 
 def shard_bounds(n_cols: int, world: int, align: int = SHARD_ALIGN) -> List[Tuple[int, int]]:
-    """Contiguous [begin, end) column ranges, every boundary except the last a multiple of `align`."""
+    """Contiguous [begin, end) column ranges. align = 1: sizes differ by at most one column; otherwise every boundary
+    except the last is a multiple of `align`."""
+    if align <= 1:
+        base, extra = divmod(n_cols, world)
+        out, a = [], 0
+        for r in range(world):
+            b = a + base + (1 if r < extra else 0)
+            out.append((a, b))
+            a = b
+        return out
     per = -(-n_cols // world)
     per = -(-per // align) * align
     return [(min(r * per, n_cols), min((r + 1) * per, n_cols)) for r in range(world)]
@@ -52,9 +61,29 @@ def merge_ranks(local: ProtocolRanks, bounds: List[Tuple[int, int]], group=None)
         mine[:, : local.bits.shape[1]] = local.bits
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine, group=group)
-        bits = torch.cat([p[:, : (e - b + 31) // 32] for p, (b, e) in zip(parts, bounds)], dim=1).contiguous()
+        bits = place_bit_columns(parts, bounds)
     return ProtocolRanks(thr=local.thr, cnt_above=cnt, bits=bits, n_cols=bounds[-1][1], col2unit=local.col2unit,
                          q_unit=local.q_unit)
+
+
+def place_bit_columns(parts: List[torch.Tensor], bounds: List[Tuple[int, int]]) -> torch.Tensor:
+    """Shard r's bit j is global column bounds[r][0] + j: shift every shard's words to their global bit offset and OR
+    them together (a shard may start in the middle of a 32-column word). Bits beyond a shard's width are zero."""
+    nq = parts[0].shape[0]
+    n_cols = bounds[-1][1]
+    out = torch.zeros((nq, (n_cols + 31) // 32 + 1), dtype=torch.int64, device=parts[0].device)
+    for p, (b, e) in zip(parts, bounds):
+        wl = (e - b + 31) // 32
+        if wl == 0:
+            continue
+        w = p[:, :wl].to(torch.int64) & 0xFFFFFFFF
+        w0, sh = b // 32, b % 32
+        out[:, w0:w0 + wl] |= (w << sh) & 0xFFFFFFFF
+        if sh:
+            out[:, w0 + 1:w0 + wl + 1] |= w >> (32 - sh)
+    out = out[:, : (n_cols + 31) // 32]
+    out = torch.where(out >= (1 << 31), out - (1 << 32), out)          # back to the int32 bit pattern
+    return out.to(parts[0].dtype).contiguous()
 
 
 def merge_topk(top_s: torch.Tensor, top_i: torch.Tensor, group=None, merge_fn=None):

@@ -65,7 +65,7 @@ def _worker(rank, world, port, n_cols, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_cols", [64, 1000, 1030])
+@pytest.mark.parametrize("n_cols", [64, 1000, 1030, 77])
 def test_sharded_merge_world2_gloo(tmp_path, n_cols):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), n_cols, str(tmp_path)), nprocs=world, join=True)
@@ -79,4 +79,27 @@ def test_shard_bounds():
         b = mmx.sharded.shard_bounds(n, w)
         assert len(b) == w and b[0][0] == 0 and b[-1][1] == n
         assert all(x[1] == y[0] for x, y in zip(b[:-1], b[1:]))
-        assert all(x[0] % 32 == 0 for x in b if x[0] < n)
+        assert max(x[1] - x[0] for x in b) - min(x[1] - x[0] for x in b) <= 1
+    assert all(x[0] % 32 == 0 for x in mmx.sharded.shard_bounds(5000, 8, align=32) if x[0] < 5000)
+
+
+def test_place_bit_columns_any_alignment():
+    """Bit columns of shards that start in the middle of a 32-column word land on their global positions."""
+    sys.path.insert(0, str(ROOT))
+    import mmx
+    rs = np.random.RandomState(4)
+    for n_cols, cuts in ((100, [0, 33, 64, 65, 100]), (5000, [0, 625, 1250, 1875, 2500, 3125, 3750, 4375, 5000]), (70, [0, 70]),
+                         (64, [0, 1, 2, 64]), (40, [0, 0, 40])):
+        above = rs.rand(7, n_cols) < 0.3
+        bounds = list(zip(cuts[:-1], cuts[1:]))
+        wmax = max((e - b + 31) // 32 for b, e in bounds)
+        parts = []
+        for b, e in bounds:
+            padded = np.zeros((7, max(wmax, 1) * 32), dtype=np.uint8)
+            padded[:, : e - b] = above[:, b:e]
+            parts.append(torch.from_numpy(np.packbits(padded, axis=1, bitorder="little").view(np.int32).copy()))
+        got = mmx.sharded.place_bit_columns(parts, bounds)
+        full = np.zeros((7, (n_cols + 31) // 32 * 32), dtype=np.uint8)
+        full[:, :n_cols] = above
+        want = torch.from_numpy(np.packbits(full, axis=1, bitorder="little").view(np.int32).copy())
+        assert got.dtype == torch.int32 and torch.equal(got, want)
