@@ -3,6 +3,7 @@
 CPU part: the oracle against golden strings produced by the reference's own v19 function, and the report's host logic.
 GPU part (-m gpu): the CUDA-backed functions against the same golden strings and the oracle."""
 import json
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -134,3 +135,22 @@ def test_pairwise_permutation_matrix_matches_reference_stream(tmp_path):
     text = mmx.generate_report(df, str(tmp_path / "r.md"), bootstrap_data=data, n_permutations=300,
                                rng=np.random.RandomState(6))
     assert "permutation test on the per-iteration bootstrap values" in text
+
+
+@pytest.mark.gpu
+def test_example_flow_end_to_end(tmp_path):
+    """examples/synthetic_benchmark.py at a small size: four models -> CSV with the reference's 42 columns -> additive
+    perm_p_* columns -> report with a permutation-test significance matrix."""
+    import subprocess, sys
+    import pandas as pd
+    import mmx
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, str(root / "examples" / "synthetic_benchmark.py"), "--images", "300", "--iterations",
+                          "60", "--patches", "64", "--permutations", "400", "--out", str(tmp_path)],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    df = pd.read_csv(tmp_path / "benchmark_v29_statistical_results.csv")
+    assert list(df.columns) == mmx.CSV_COLUMNS and len(df) == 4
+    df2 = pd.read_csv(tmp_path / "benchmark_v29_with_permutation_tests.csv")
+    assert list(df2.columns)[:42] == mmx.CSV_COLUMNS and "perm_p_T2I_R@1" in df2.columns
+    assert "permutation test on the per-iteration bootstrap values" in (tmp_path / "analysis_report.md").read_text()
