@@ -678,3 +678,46 @@ def test_run_bootstrap_colpali_small(mmx_mod):
         bits = np.unpackbits(ranks[p].bits.cpu().numpy().view(np.uint8), axis=1, bitorder="little")[:, : len(col_unit)]
         sets[p] = (bits, col_unit, np.arange(n))
     assert np.array_equal(got, oracle.bootstrap_identity(sets, si, n))
+
+
+def test_run_bootstrap_benchmark_reference_signature(mmx_mod):
+    """main.py:478-667 through the drop-in signature, with stand-ins for the upstream pieces it keeps (dataset walk,
+    image cache, encoders): items without an image or with fewer than five captions are skipped exactly like
+    main.py:508-525, the row has the reference's 42 columns, QPS comes from the encoding time only (main.py:653-660),
+    and an empty dataset returns {} (main.py:527-529)."""
+    n, dim = 120, 64
+    img, all_txt = synth_dense(n, dim, 3.0, seed=31)
+    dataset = []
+    for i in range(n):
+        dataset.append({"id": i, "sentences": [f"a red cat {i} {c}" for c in range(5 + (i % 2))]})
+    dataset.insert(7, {"id": -1, "sentences": ["only", "four", "captions", "here"]})      # skipped: < 5 captions
+    dataset.insert(30, {"id": -2, "sentences": [f"x{c}" for c in range(5)], "broken": True})   # skipped: no image
+    cap_index = {f"a red cat {i} {c}": 5 * i + c for i in range(n) for c in range(5)}
+
+    def load_cached_image(item):
+        return None if item.get("broken") else item["id"]
+
+    def get_all_captions(item, col):
+        return item[col]
+
+    calls = []
+
+    def encode_data(model, processor, m_info, images, texts):
+        calls.append((len(images), len(texts)))
+        ie = img[torch.tensor(images, dtype=torch.long)] if images else None
+        te = all_txt[torch.tensor([cap_index[t] for t in texts], dtype=torch.long)] if texts else None
+        return ie, te
+
+    m_info = {"type": "dense", "name": "Fake"}
+    row = mmx_mod.run_bootstrap_benchmark(None, None, m_info, dataset, 25, encode_data=encode_data,
+                                          load_cached_image=load_cached_image, get_all_captions=get_all_captions)
+    assert list(row.keys()) == mmx_mod.CSV_COLUMNS
+    assert calls == [(n, 0), (0, n), (0, 5 * n)]
+    assert row["QPS"] == row["Img_per_sec"] == n / row["Encoding_Time"]
+    assert 0 < row["T2I_R@1_lower"] <= row["T2I_R@1_mean"] <= row["T2I_R@1_upper"] <= 100
+    assert row["_failure_analysis"]["accuracy_has_color"] == row["_failure_analysis"]["overall_accuracy"]   # every caption says "red"
+    assert mmx_mod.run_bootstrap_benchmark(None, None, m_info, [{"sentences": ["a"] * 5, "broken": True}], 5,
+                                           encode_data=encode_data, load_cached_image=load_cached_image,
+                                           get_all_captions=get_all_captions) == {}
+    with pytest.raises(TypeError):
+        mmx_mod.run_bootstrap_benchmark(None, None, m_info, dataset, 5)            # upstream hooks are mandatory
