@@ -112,11 +112,15 @@ def _flatten_any(x, dev: torch.device) -> Tuple[torch.Tensor, torch.Tensor, np.n
 
 def _pad_flags(lens: np.ndarray, chunk: int = CHUNK) -> np.ndarray:
     """1 where pad_sequence adds a zero row to the document inside its chunk of 10 (main.py:465-467)."""
-    flags = np.zeros(len(lens), dtype=np.uint8)
-    for j in range(0, len(lens), chunk):
-        c = lens[j:j + chunk]
-        flags[j:j + chunk] = (c < c.max()).astype(np.uint8)
-    return flags
+    lens = np.asarray(lens, dtype=np.int64)
+    n = len(lens)
+    if n == 0:
+        return np.zeros(0, dtype=np.uint8)
+    full = -(-n // chunk) * chunk
+    padded = np.full(full, -1, dtype=np.int64)          # the last chunk may be short: fillers never win the max
+    padded[:n] = lens
+    cmax = padded.reshape(-1, chunk).max(axis=1)
+    return (lens < np.repeat(cmax, chunk)[:n]).astype(np.uint8)
 
 
 def _gt_dev(gt_sets: Sequence[Sequence[int]], dev: torch.device):
