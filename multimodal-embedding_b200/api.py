@@ -98,7 +98,17 @@ def _flatten(items: List[torch.Tensor], dev: torch.device) -> Tuple[torch.Tensor
     lens = np.array([int(t.shape[0]) for t in items], dtype=np.int64)
     off = np.zeros(len(items) + 1, dtype=np.int32)
     off[1:] = np.cumsum(lens)
-    flat = torch.cat([_as_bf16(t, "ColPali embeddings") for t in items], dim=0) if items else torch.empty(0, 128, dtype=torch.bfloat16)
+    if not items:
+        flat = torch.empty(0, 128, dtype=torch.bfloat16)
+    elif items[0].is_cuda:
+        flat = torch.cat([_as_bf16(t, "ColPali embeddings") for t in items], dim=0)
+    else:
+        # the reference hands over 30 000 small CPU tensors: gather them straight into ONE pinned buffer (a single
+        # pass over the 1.4 GB instead of cat + pin), from where the upload is asynchronous
+        for t in items:
+            _as_bf16(t, "ColPali embeddings")
+        flat = torch.empty((int(off[-1]), int(items[0].shape[1])), dtype=torch.bfloat16, pin_memory=True)
+        torch.cat(list(items), dim=0, out=flat)
     return _h2d(flat, dev), _np_h2d(off, dev, torch.int32), lens
 
 
