@@ -321,15 +321,14 @@ static int launch_dense(const void* Q, int64_t nq, const void* G, int64_t ng, in
     if (make_tmap_bf16_sw128(&tq, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, BM) != 0) return -4;
     if (make_tmap_bf16_sw128(&tg, G, (uint64_t)ng, (uint64_t)d, (uint64_t)d, BN) != 0) return -4;
     const size_t smem_bytes = sizeof(Smem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static const char attr_set_tag = 0;
+    if (first_use_on_device(&attr_set_tag)) {
         MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_THRESHOLD>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_COUNT>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_GROUPMAX>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        attr_set = true;
     }
     const int sms = sm_count();
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;

@@ -917,11 +917,10 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
     MMX_CHECK_CUDA(cudaGetLastError());
 
     const size_t smem_bytes = sizeof(Smem) + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static const char attr_set_tag = 0;
+    if (first_use_on_device(&attr_set_tag)) {
         MMX_CHECK_CUDA(cudaFuncSetAttribute(maxsim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         MMX_CHECK_CUDA(cudaFuncSetAttribute(maxsim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        attr_set = true;
     }
     const long long n_items = (long long)p.n_mpairs * p.n_chunks;
     const int grid = (int)(n_items < sms ? n_items : sms);

@@ -2,6 +2,8 @@
 
 #include <cstring>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "../../include/mmx.h"
 
@@ -56,13 +58,22 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint
     return 0;
 }
 
+bool first_use_on_device(const void* tag) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> seen;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& e : seen)
+        if (e.first == tag && e.second == dev) return false;
+    seen.emplace_back(tag, dev);
+    return true;
+}
+
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    }
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     return n;
 }
 

@@ -38,4 +38,8 @@ int make_tmap_bf16_sw128(CUtensorMap* out, const void* base, uint64_t rows, uint
 
 int sm_count();
 
+// true the first time it is called for `tag` on the CURRENT device (kernel attributes such as the dynamic shared-memory
+// limit are per device: a process that drives several GPUs has to set them on each one)
+bool first_use_on_device(const void* tag);
+
 }  // namespace mmx

@@ -332,11 +332,10 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
     int32_t* prefix = reinterpret_cast<int32_t*>(ws + pl.off_d - 256);
     const int n1 = n - 1;
     const size_t smem_tab = (size_t)(RW + CT) * 4 + 3 * (size_t)((n1 + 1) & ~1) * 2;
-    static bool tab_attr = false;
-    if (!tab_attr) {
+    static const char tab_attr_tag = 0;
+    if (first_use_on_device(&tab_attr_tag)) {
         MMX_CHECK_CUDA(cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (RW + CT) * 4 + 3 * MAX_N * 2));
-        tab_attr = true;
     }
     tables_kernel<<<(unsigned)pl.n_chunks, CT, smem_tab, stream>>>(words, n_words, n1, tab);
     MMX_CHECK_CUDA(cudaGetLastError());
@@ -352,11 +351,10 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
     dim3 gt((unsigned)((P + 31) / 32), (unsigned)((n + 31) / 32));
     transpose_kernel<<<gt, 256, 0, stream>>>(arr, n, P, pi);
     const size_t smem = (size_t)n * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static const char attr_set_tag = 0;
+    if (first_use_on_device(&attr_set_tag)) {
         MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_N * 8));
         MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_N * 8));
-        attr_set = true;
     }
     compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, nullptr, comp, nullptr);
     compose_scan_kernel<<<1, 512, smem, stream>>>(comp, n, pl.n_blocks, prefix);

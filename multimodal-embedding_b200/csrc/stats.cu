@@ -264,11 +264,9 @@ extern "C" int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_
     if (B == 0) return 0;
     const int in_smem = n_units <= 200 * 1024;
     const size_t smem = in_smem ? (size_t)((n_units + 15) & ~15ll) : 0;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    static const char boot_tag = 0;
+    if (smem > 48 * 1024 && first_use_on_device(&boot_tag))
         MMX_CHECK_CUDA(cudaFuncSetAttribute(boot_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
-        smem_set = 200 * 1024 + 16;
-    }
     boot_counts_kernel<<<B, 256, smem, stream>>>(list_t, L, cnt_above, above_bits, words_per_row, col2unit, q_unit, mult,
                                                  n_units, nq, in_smem, correct, q_hits1);
     MMX_CHECK_CUDA(cudaGetLastError());
@@ -286,11 +284,9 @@ static int launch_gather_mean(const double* data, int n_data, const int32_t* idx
     if (n2 > 0 && make_program(n2, &p2) != 0) return -2;
     const int in_smem = (size_t)n_data * 8 <= 200 * 1024;
     const size_t smem = in_smem ? (size_t)n_data * 8 : 0;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    static const char gather_tag = 0;
+    if (smem > 48 * 1024 && first_use_on_device(&gather_tag))
         MMX_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        smem_set = 200 * 1024;
-    }
     gather_mean_kernel<<<dim3((R + 127) / 128, batch), 128, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, p1, p2,
                                                                             in_smem, out);
     MMX_CHECK_CUDA(cudaGetLastError());
