@@ -310,6 +310,7 @@ __device__ __forceinline__ void reduce_doc(Smem& s, const Params& p, Reducer& r,
     for (int k = 0; k < BM / 32; ++k) {
         const int row = k * 32 + lane;
         float x = fmaxf(s.stage[g][slot][0][row], s.stage[g][slot][1][row]);
+        if (x == -INFINITY) x = 0.0f;  // a document without patches: the reference pads it with zero rows -> 0
         v[k] = zero ? fmaxf(x, 0.0f) : x;
     }
     __syncwarp();

@@ -36,6 +36,11 @@ def test_empty_inputs(mmx_mod):
     dd_off = torch.tensor([0, 40, 40], dtype=torch.int32, device=dev)
     s = ops.maxsim_scores(docs, q_off, docs, dd_off)
     assert torch.all(s[0] == 0) and torch.all(s[:, 1] == 0) and torch.all(s[1:, 0] > 0)
+    # the same with long documents (the T2I kernel variant): an empty document among 300-row ones scores 0
+    long_docs = _rnd(900, 128, 3).to(dev)
+    ld_off = torch.tensor([0, 300, 300, 600, 900], dtype=torch.int32, device=dev)
+    s2 = ops.maxsim_scores(docs, d_off, long_docs, ld_off)
+    assert torch.all(s2[:, 1] == 0) and torch.all(torch.isfinite(s2)) and torch.all(s2[:, 0] > 0)
     Q = _rnd(5, 64, 2).to(dev)
     gt_off = torch.arange(6, dtype=torch.int32, device=dev)
     r = ops.dense_rank(Q, torch.empty(0, 64, dtype=torch.bfloat16, device=dev), gt_off, torch.zeros(5, dtype=torch.int32, device=dev))
@@ -83,3 +88,15 @@ def test_argument_errors_are_exceptions(mmx_mod):
         mmx_mod.ops.DeviceRng(np.random.RandomState(0)).shuffle_indices(20000, 3)     # beyond the device-shuffle limit
     # the library keeps working after an error
     assert float(ops.dense_scores(_rnd(3, 64, 1).to(dev), _rnd(3, 64, 1).to(dev)).diagonal().min()) > 0.99
+
+
+@pytest.mark.parametrize("seed", [0, 2])
+def test_maxsim_randomised_shapes(seed):
+    """dev/fuzz_maxsim.py: random ragged shapes (empty items, padding flags, both kernel variants) vs a torch fp32
+    restatement; seed 2 holds the empty-document-among-long-documents case that once produced -inf."""
+    import subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, str(root / "dev" / "fuzz_maxsim.py"), str(seed), "40"], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "random cases ok" in res.stdout, res.stdout[-500:] + res.stderr[-1500:]
