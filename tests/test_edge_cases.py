@@ -100,3 +100,14 @@ def test_maxsim_randomised_shapes(seed):
     res = subprocess.run([sys.executable, str(root / "dev" / "fuzz_maxsim.py"), str(seed), "40"], capture_output=True,
                          text=True, timeout=600)
     assert res.returncode == 0 and "random cases ok" in res.stdout, res.stdout[-500:] + res.stderr[-1500:]
+
+
+def test_rank_and_statistics_randomised_shapes():
+    """dev/fuzz_rank_stats.py: random problems for K1 / KR / KT / tie report / K3 / K4 / K6 / K6s, every integer and
+    every double compared bit for bit with torch / numpy restatements."""
+    import subprocess, sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    res = subprocess.run([sys.executable, str(root / "dev" / "fuzz_rank_stats.py"), "3", "12"], capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "random cases ok" in res.stdout, res.stdout[-500:] + res.stderr[-1500:]
