@@ -299,11 +299,18 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
     out: Dict[str, ops.ProtocolRanks] = {}
     if m_info["type"] == "colpali":
         n = len(img_embeds)
-        i_flat, i_off, i_lens = _flatten_any(img_embeds, dev)
-        t_flat, t_off, t_lens = _flatten_any(t2i_txt_embeds, dev)
         a_flat, a_off, a_lens = _flatten_any(all_txt_embeds, dev)
-        fl_i, fl_a = _pad_flags(i_lens), _pad_flags(a_lens)
-        s_t2i = ops.maxsim_scores(t_flat, t_off, i_flat, i_off, _np_h2d(fl_i, dev, torch.uint8) if fl_i.any() else None)
+        if isinstance(img_embeds, FlatMultiVector) and isinstance(t2i_txt_embeds, FlatMultiVector):
+            # host-resident images: their upload overlaps the T2I scoring, the device copy is reused for I2T
+            kept: dict = {}
+            s_t2i = _maxsim_streamed(t2i_txt_embeds, img_embeds, dev, keep=kept)
+            (i_flat, i_off), i_lens = kept["d"], img_embeds.lens
+        else:
+            i_flat, i_off, i_lens = _flatten_any(img_embeds, dev)
+            t_flat, t_off, t_lens = _flatten_any(t2i_txt_embeds, dev)
+            fl_i = _pad_flags(i_lens)
+            s_t2i = ops.maxsim_scores(t_flat, t_off, i_flat, i_off, _np_h2d(fl_i, dev, torch.uint8) if fl_i.any() else None)
+        fl_a = _pad_flags(a_lens)
         s_i2t = ops.maxsim_scores(i_flat, i_off, a_flat, a_off, _np_h2d(fl_a, dev, torch.uint8) if fl_a.any() else None)
         id_off, id_idx = _identity_gt(n, dev)
         b_off, b_idx = _block_gt(n, caps_per_img, dev)
@@ -514,10 +521,11 @@ H2D_DOC_CHUNKS = 8   # host-resident documents are uploaded in this many pieces,
 
 
 def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device,
-                     flags: Optional[np.ndarray] = None) -> torch.Tensor:
+                     flags: Optional[np.ndarray] = None, keep: Optional[dict] = None) -> torch.Tensor:
     """K2 over documents that still live in host memory: the upload of document chunk c+1 (copy stream, pinned
     source) overlaps the scoring of chunk c, so PCIe time hides behind the tensor cores. Returns fp32 [nq, nd].
-    `flags`: the documents' zero-padding flags when they are not those of this list taken alone (a shard)."""
+    `flags`: the documents' zero-padding flags when they are not those of this list taken alone (a shard).
+    `keep`: filled with the device copies ({"q": (flat, off), "d": (flat, off)}) for callers that score again."""
     nq, nd = len(qv), len(dv)
     if flags is None:
         flags = _pad_flags(dv.lens)                   # chunk-of-10 padding flags of the WHOLE list (main.py:465)
@@ -525,27 +533,40 @@ def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device
     n_chunks = 1 if dv.flat.is_cuda else max(1, min(H2D_DOC_CHUNKS, nd // 64))
     if n_chunks == 1:
         d_flat, d_off = dv.to_device(dev)
+        if keep is not None:
+            keep["q"], keep["d"] = (q_flat, q_off), (d_flat, d_off)
         return ops.maxsim_scores(q_flat, q_off, d_flat, d_off, _np_h2d(flags, dev, torch.uint8) if flags.any() else None)
     S = torch.empty((nq, nd), dtype=torch.float32, device=dev)
     main, copy = torch.cuda.current_stream(), _aux_stream(dev, "copy")
     step = -(-nd // n_chunks)
+    # one device buffer for all documents (allocated on the main stream, filled chunk by chunk on the copy stream):
+    # every chunk is scored from its slice, and the whole matrix is there afterwards for the role-swapped pass
+    src = _as_bf16(dv.flat, "multi-vector embeddings")
+    if not src.is_pinned():
+        pinned = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        pinned.copy_(src)
+        src = pinned
+    d_all = torch.empty(src.shape, dtype=torch.bfloat16, device=dev)
+    off_h = np.zeros(nd + 1, dtype=np.int64)
+    off_h[1:] = np.cumsum(dv.lens)
+    d_off_all = _np_h2d(off_h.astype(np.int32), dev, torch.int32)
+    d_zero_all = _np_h2d(flags, dev, torch.uint8) if flags.any() else None
     staged = []
     copy.wait_stream(main)
     with torch.cuda.stream(copy):
         for a in range(0, nd, step):
             b = min(nd, a + step)
-            part = dv.slice(a, b)
-            d_flat, d_off = part.to_device(dev)
-            d_zero = _np_h2d(flags[a:b], dev, torch.uint8) if flags[a:b].any() else None
+            r0, r1 = int(off_h[a]), int(off_h[b])
+            d_all[r0:r1].copy_(src[r0:r1], non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(copy)
-            staged.append((a, b, d_flat, d_off, d_zero, ready))
-    for a, b, d_flat, d_off, d_zero, ready in staged:
+            staged.append((a, b, r0, r1, ready))
+    for a, b, r0, r1, ready in staged:
         main.wait_event(ready)
-        for t in (d_flat, d_off, d_zero):
-            if t is not None:
-                t.record_stream(main)
-        ops.maxsim_scores(q_flat, q_off, d_flat, d_off, d_zero, out=S[:, a:b])
+        sub_off = (d_off_all[a:b + 1] - r0).contiguous()
+        ops.maxsim_scores(q_flat, q_off, d_all[r0:r1], sub_off, None if d_zero_all is None else d_zero_all[a:b], out=S[:, a:b])
+    if keep is not None:
+        keep["q"], keep["d"] = (q_flat, q_off), (d_all, d_off_all)
     return S
 
 
