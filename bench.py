@@ -455,7 +455,17 @@ def dense_section(dev, K, W, cpu_iters=2):
         per = oracle.bootstrap_rescore_reference(img, t2i, all_txt, cpu_iters, rng=np.random.RandomState(42))
         cpu_s = (time.perf_counter() - t0) / cpu_iters
         same = all(per[i][k] == row["_bootstrap_values"][k][i] for i in range(cpu_iters) for k in mmx.METRIC_KEYS)
+        v1, v2 = row["_bootstrap_values"]["T2I_R@1"], row["_bootstrap_values"]["I2T_Sym_R@1"]
+        t0 = time.perf_counter()
+        ci_ref = oracle.bootstrap_confidence_interval(v1, rng=np.random.RandomState(5))      # main.py:259-278
+        ci_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        p_ref = oracle.permutation_test(v1, v2, rng=np.random.RandomState(7))               # main.py:281-302
+        perm_s = time.perf_counter() - t0
+        ci_gpu = mmx.bootstrap_confidence_interval(v1, rng=np.random.RandomState(5))
         cpu = {"kind": "port", "cores": os.cpu_count() or 1, "s_per_iteration": cpu_s,
+               "bootstrap_confidence_interval_s": ci_s, "permutation_test_s": perm_s,
+               "ci_and_p_equal_gpu": bool(ci_ref == ci_gpu and float(p_ref) == float(p)),
                "sample": f"{cpu_iters} of {N_ITER} bootstrap iterations (gather + rescore + compute_metrics_detailed)",
                "extrapolated_s_for_1000_iterations": cpu_s * N_ITER,
                "first_iterations_equal_gpu_row": bool(same)}
