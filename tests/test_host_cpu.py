@@ -78,3 +78,15 @@ def test_flat_multivector_disk_cache_roundtrip(tmp_path):
     assert all(torch.equal(a.view(torch.int16), b.view(torch.int16)) for a, b in zip(back.to_list(), items))
     part = back.slice(2, 4)
     assert len(part) == 2 and part.flat.shape[0] == 17 + 1030
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (or the examples) may import or execute it."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    files = list((root / "multimodal-embedding_b200").glob("*.py")) + list((root / "examples").glob("*.py")) + [root / "mmx.py"]
+    bad = [f.name for f in files if re.search(r"^\s*(import|from)\s+oracle\b", f.read_text(), flags=re.M)]
+    assert bad == []
+    csrc = (root / "multimodal-embedding_b200" / "csrc")
+    assert not any("oracle" in p.read_text() for p in list(csrc.glob("*.cu")) + list(csrc.glob("*.cuh")))
