@@ -38,8 +38,9 @@
 // reference's zero padding). Boundaries then fall on 4-column groups and are the same for every thread, so the drain
 // is branch-uniform: 8 group maxima per 32-column chunk, a running maximum, and one shared-memory store per closed
 // document into M[accumulator][slot][row] (at most 16 documents end inside one 256-column tile). Warps 4-7 drain
-// accumulator 0 and warps 8-11 accumulator 1 (all 256 columns each: no half merging), and the reducer sums the rows
-// of a whole tile's documents at once, one lane per document, instead of one latency-bound shuffle tree per document.
+// accumulator 0 and warps 8-11 accumulator 1 (all 256 columns each: no half merging), and two reducer warps (2 and 3,
+// one per accumulator) sum the rows of a whole tile's documents at once, two lanes per document, instead of one
+// latency-bound shuffle tree per document.
 #include <cfloat>
 #include <climits>
 #include <cstdlib>
