@@ -40,6 +40,9 @@ for case in range(n_cases):
     assert torch.equal(rk.thr, r.thr) and torch.equal(rk.cnt_above, r.cnt_above) and torch.equal(rk.bits, r.bits), ("KR", case)
     k = int(rs.choice([1, 5, 10, 32]))
     ts, ti = ops.dense_topk(Q, G, k, g_base=g_base)
+    rt = ops.dense_rank(Q, G, off_d, idx_d, g_base=g_base, top_k=k)                 # fused COUNT + group maxima
+    assert torch.equal(rt.top_s, ts) and torch.equal(rt.top_i, ti), ("rank_topk lists", case, nq, ng, d, k)
+    assert torch.equal(rt.cnt_above, r.cnt_above) and torch.equal(rt.bits, r.bits) and torch.equal(rt.thr, r.thr), ("rank_topk rank", case)
     ks, ki = ops.topk_from_scores(S, k, g_base=g_base)
     assert torch.equal(ts, ks) and torch.equal(ti, ki), ("KT fused vs scores", case, nq, ng, d, k)
     sv, si = torch.sort(Sc, dim=1, descending=True, stable=True)

@@ -26,13 +26,12 @@ off = torch.arange(N + 1, dtype=torch.int32, device=dev); idx = torch.arange(N, 
 def step(topk):
     loc = ops.dense_rank(txt, G, off, idx, want_bits=False, g_base=a, threshold_only=True)
     thr = sharded.merge_thresholds(loc.thr)
-    loc = ops.dense_rank(txt, G, off, idx, want_bits=False, g_base=a, thr=thr)
+    loc = ops.dense_rank(txt, G, off, idx, want_bits=False, g_base=a, thr=thr, top_k=10 if topk else None)
     cnt = loc.cnt_above.clone()
     if world > 1: dist.all_reduce(cnt)
     res = [int((cnt < k).sum()) for k in (1, 5, 10)]
     if topk:
-        ts, ti = ops.dense_topk(txt, G, 10, g_base=a)
-        ts, ti = sharded.merge_topk(ts, ti)
+        ts, ti = sharded.merge_topk(loc.top_s, loc.top_i)
         res.append(int((ti[:, 0].long() == torch.arange(N, device=dev)).sum()))
     return res
 for topk in (False, True):

@@ -103,6 +103,12 @@ int mmx_topk_from_scores(const float* scores, int64_t nq, int64_t ng, int64_t ld
 int mmx_dense_topk_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes);
 int mmx_dense_topk(const void* Q, int64_t nq, const void* G, int64_t ng, int d, int64_t g_base, int k, float* top_s,
                    int32_t* top_i, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+/* mmx_dense_rank (MMX_MODE_COUNT) and the top-k lists in one call: the COUNT pass also stores the group maxima, so the
+ * lists cost one extra GEMM pass instead of two. thr = merged thresholds, cnt_above zeroed by the caller. */
+int mmx_dense_rank_topk(const void* Q, int64_t nq, const void* G, int64_t ng, int d, const int32_t* gt_off,
+                        const int32_t* gt_idx, int64_t g_base, float* thr, int32_t* cnt_above, uint32_t* above_bits,
+                        int64_t words_per_row, int k, float* top_s, int32_t* top_i, void* workspace,
+                        size_t workspace_bytes, cudaStream_t stream);
 int mmx_topk_select(const float* cand_s, const int32_t* cand_i, const int32_t* cand_n, int64_t nq, int cap, int k,
                     float* top_s, int32_t* top_i, cudaStream_t stream);
 int mmx_merge_topk(const float* gathered_s, const int32_t* gathered_i, int n_shards, int64_t nq, int k, float* top_s,

@@ -95,6 +95,13 @@ _SIGNATURES = {
         _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int64, _c.c_int,   # Q, nq, G, ng, d, g_base, k
         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p,                    # top_s, top_i, ws, bytes, stream
     ]),
+    "mmx_dense_rank_topk": (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int,   # Q, nq, G, ng, d
+        _c.c_void_p, _c.c_void_p, _c.c_int64,                         # gt_off, gt_idx, g_base
+        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64,            # thr, cnt_above, above_bits, words_per_row
+        _c.c_int, _c.c_void_p, _c.c_void_p,                           # k, top_s, top_i
+        _c.c_void_p, _c.c_size_t, _c.c_void_p,                        # workspace, bytes, stream
+    ]),
     "mmx_topk_select": (_c.c_int, [
         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int,    # cand_s, cand_i, cand_n, nq, cap, k
         _c.c_void_p, _c.c_void_p, _c.c_void_p,                                    # top_s, top_i, stream

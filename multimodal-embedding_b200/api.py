@@ -332,12 +332,10 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
         n = img.shape[0]
         id_off, id_idx = _identity_gt(n, dev)
         b_off, b_idx = _block_gt(n, caps_per_img, dev)
-        out["T2I"] = ops.dense_rank(t2i, img, id_off, id_idx, want_bits)         # [n_txt, n_img]   main.py:620
-        out["I2T"] = ops.dense_rank(img, allc, b_off, b_idx, want_bits)          # [n_img, 5 n_img] main.py:622 (D1 fixed)
-        out["I2T_Sym"] = ops.dense_rank(img, t2i, id_off, id_idx, want_bits)     # = scores_t2i.t() main.py:624
-        if want_top10:
-            for name, (qq, gg) in (("T2I", (t2i, img)), ("I2T", (img, allc)), ("I2T_Sym", (img, t2i))):
-                out[name].top_s, out[name].top_i = ops.dense_topk(qq, gg, 10)
+        tk = 10 if want_top10 else None
+        out["T2I"] = ops.dense_rank(t2i, img, id_off, id_idx, want_bits, top_k=tk)       # [n_txt, n_img]   main.py:620
+        out["I2T"] = ops.dense_rank(img, allc, b_off, b_idx, want_bits, top_k=tk)        # [n_img, 5 n_img] main.py:622 (D1 fixed)
+        out["I2T_Sym"] = ops.dense_rank(img, t2i, id_off, id_idx, want_bits, top_k=tk)   # = scores_t2i.t() main.py:624
         if want_ties:
             for name, (qq, gg), (go, gi) in (("T2I", (t2i, img), (id_off, id_idx)), ("I2T", (img, allc), (b_off, b_idx)),
                                              ("I2T_Sym", (img, t2i), (id_off, id_idx))):

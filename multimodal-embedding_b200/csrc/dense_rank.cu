@@ -229,6 +229,15 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
                     bits &= cmask;
                     cnt += __popc(bits);
+                    if (p.grp_max != nullptr) {  // fused group maxima for the top-k bound (mmx_dense_rank_topk)
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) m = fmaxf(m, j < nvalid ? __uint_as_float(v[j]) : -INFINITY);
+                        if (p.grp_tile)
+                            best = fmaxf(best, m);
+                        else if (valid_row && nvalid > 0)
+                            p.grp_max[q * p.n_grp + (c0 >> 5)] = m;
+                    }
                     const long long w = (c0 >> 5);
                     if (p.above_bits != nullptr && valid_row && w < p.words_per_row)
                         p.above_bits[q * p.words_per_row + w] = bits;
@@ -271,6 +280,7 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             if (MODE == MMX_MODE_COUNT) {
                 if (valid_row && cnt > 0) atomicAdd(p.cnt_above + q, cnt);
+                if (p.grp_max != nullptr && p.grp_tile && valid_row) p.grp_max[q * p.n_grp + n_tile] = best;
             } else if (MODE == MMX_MODE_GROUPMAX) {
                 if (p.grp_tile && valid_row) p.grp_max[q * p.n_grp + n_tile] = best;
             } else if (valid_row && best > -INFINITY) {
@@ -458,6 +468,15 @@ overflow_rows_kernel(const __nv_bfloat16* __restrict__ Q, const __nv_bfloat16* _
     }
 }
 
+struct TopkPlan;
+}  // namespace dense
+}  // namespace mmx
+static int topk_from_group_maxima(const void* Q, int64_t nq, const void* G, int64_t ng, int d, int64_t g_base, int k,
+                                  float* top_s, int32_t* top_i, uint8_t* ws, const mmx::dense::TopkPlan& t,
+                                  cudaStream_t stream);
+namespace mmx {
+namespace dense {
+
 struct TopkPlan {
     bool small;
     int grp_tile;
@@ -527,14 +546,28 @@ extern "C" int mmx_dense_topk(const void* Q, int64_t nq, const void* G, int64_t 
         return mmx_topk_from_scores(S, nq, ng, ng, g_base, k, top_s, top_i, stream);
     }
     float* grp = reinterpret_cast<float*>(ws + t.off_grp);
-    int32_t* cand_n = reinterpret_cast<int32_t*>(ws + t.off_candn);
-    float* cand_s = reinterpret_cast<float*>(ws + t.off_cs);
-    int32_t* cand_i = reinterpret_cast<int32_t*>(ws + t.off_ci);
     p.mode = MMX_MODE_GROUPMAX;
     p.grp_max = grp;
     p.n_grp = t.n_grp;
     p.grp_tile = t.grp_tile;
     if (int rc = launch_dense(Q, nq, G, ng, d, p, stream)) return rc;
+    return topk_from_group_maxima(Q, nq, G, ng, d, g_base, k, top_s, top_i, ws, t, stream);
+}
+
+// second half of the matrix-free top-k: bar from the group maxima, candidate pass, selection, exact overflow rows
+static int topk_from_group_maxima(const void* Q, int64_t nq, const void* G, int64_t ng, int d, int64_t g_base, int k,
+                                  float* top_s, int32_t* top_i, uint8_t* ws, const TopkPlan& t, cudaStream_t stream) {
+    float* bar = reinterpret_cast<float*>(ws + t.off_bar);
+    int32_t* cnt = reinterpret_cast<int32_t*>(ws + t.off_cnt);
+    float* grp = reinterpret_cast<float*>(ws + t.off_grp);
+    int32_t* cand_n = reinterpret_cast<int32_t*>(ws + t.off_candn);
+    float* cand_s = reinterpret_cast<float*>(ws + t.off_cs);
+    int32_t* cand_i = reinterpret_cast<int32_t*>(ws + t.off_ci);
+    Params p;
+    if (base_params(p, nq, ng, d) != 0) return -2;
+    p.g_base = g_base;
+    p.thr = bar;
+    p.cnt_above = cnt;
     kth_group_bar_kernel<<<(unsigned)((nq + 7) / 8), 256, 0, stream>>>(grp, nq, t.n_grp, k, bar);
     MMX_CHECK_CUDA(cudaGetLastError());
     MMX_CHECK_CUDA(cudaMemsetAsync(cand_n, 0, (size_t)nq * 4, stream));
@@ -552,4 +585,50 @@ extern "C" int mmx_dense_topk(const void* Q, int64_t nq, const void* G, int64_t 
         k, top_s, top_i);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+
+// K1 ranking COUNT pass and the top-k in one call: the COUNT pass (which every tile goes through anyway) also
+// stores the group maxima, so the lists cost ONE extra GEMM pass (the candidate pass) instead of two.
+// thr must hold the (shard-merged) thresholds, cnt_above must be zeroed by the caller, exactly as for mmx_dense_rank
+// in MMX_MODE_COUNT. workspace: mmx_dense_topk_workspace_bytes(nq, ng).
+extern "C" int mmx_dense_rank_topk(const void* Q, int64_t nq, const void* G, int64_t ng, int d, const int32_t* gt_off,
+                                   const int32_t* gt_idx, int64_t g_base, float* thr, int32_t* cnt_above,
+                                   uint32_t* above_bits, int64_t words_per_row, int k, float* top_s, int32_t* top_i,
+                                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    MMX_REQUIRE(nq >= 0 && ng >= 0 && d >= 8 && d % 8 == 0, "bad shape nq=%lld ng=%lld d=%d (d must be a multiple of 8)",
+                (long long)nq, (long long)ng, d);
+    MMX_REQUIRE(k >= 1 && k <= topk::MAX_K, "k must be in [1, %d]", topk::MAX_K);
+    MMX_REQUIRE(thr != nullptr && cnt_above != nullptr && top_s != nullptr && top_i != nullptr, "NULL argument");
+    MMX_REQUIRE(above_bits == nullptr || words_per_row >= (ng + 31) / 32, "words_per_row too small");
+    MMX_REQUIRE(g_base + ng < (1ll << 31), "column index does not fit int32");
+    if (nq == 0) return 0;
+    if (mmx_device_check() != 0) return -3;
+    if (ng == 0) return mmx_topk_from_scores(nullptr, nq, 0, 0, g_base, k, top_s, top_i, stream);
+    const TopkPlan t = plan_topk(nq, ng);
+    MMX_REQUIRE(workspace != nullptr && workspace_bytes >= t.total, "workspace too small: need %zu bytes", t.total);
+    uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+    Params p;
+    if (base_params(p, nq, ng, d) != 0) return -2;
+    p.gt_off = gt_off;
+    p.gt_idx = gt_idx;
+    p.g_base = g_base;
+    p.thr = thr;
+    p.cnt_above = cnt_above;
+    p.above_bits = above_bits;
+    p.words_per_row = words_per_row;
+    p.mode = MMX_MODE_COUNT;
+    if (t.small) {
+        // few columns: the COUNT pass also writes the scores into the workspace and the lists are read off them
+        float* S = reinterpret_cast<float*>(ws + t.off_grp);
+        p.scores = S;
+        p.ld_scores = ng;
+        if (int rc = launch_dense(Q, nq, G, ng, d, p, stream)) return rc;
+        return mmx_topk_from_scores(S, nq, ng, ng, g_base, k, top_s, top_i, stream);
+    }
+    p.grp_max = reinterpret_cast<float*>(ws + t.off_grp);
+    p.n_grp = t.n_grp;
+    p.grp_tile = t.grp_tile;
+    if (int rc = launch_dense(Q, nq, G, ng, d, p, stream)) return rc;
+    return topk_from_group_maxima(Q, nq, G, ng, d, g_base, k, top_s, top_i, ws, t, stream);
 }

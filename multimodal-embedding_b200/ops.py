@@ -124,11 +124,12 @@ def _alloc_rank(nq: int, n_cols: int, device, want_bits: bool):
 
 def dense_rank(Q: torch.Tensor, G: torch.Tensor, gt_off: torch.Tensor, gt_idx: torch.Tensor, want_bits: bool = True,
                want_scores: bool = False, g_base: int = 0, thr: Optional[torch.Tensor] = None,
-               threshold_only: bool = False) -> ProtocolRanks:
+               threshold_only: bool = False, top_k: Optional[int] = None) -> ProtocolRanks:
     """K1. Q [nq,d], G [ng,d] bf16 CUDA; GT CSR int32 CUDA (global column ids) -> thresholds, counts, bitmask.
 
     With `thr` given the threshold pass is skipped (multi-GPU: thresholds were max-reduced over shards first);
-    `threshold_only` stops after the threshold pass."""
+    `threshold_only` stops after the threshold pass. `top_k` also returns the top-k lists (``top_s`` / ``top_i``): the
+    COUNT pass stores the group maxima on its way, so they cost one more GEMM pass, not two."""
     _need_cuda(Q, G, gt_off, gt_idx, thr)
     if Q.dtype != torch.bfloat16 or G.dtype != torch.bfloat16:
         raise TypeError("dense rank kernel takes bf16 embeddings")
@@ -146,11 +147,23 @@ def dense_rank(Q: torch.Tensor, G: torch.Tensor, gt_off: torch.Tensor, gt_idx: t
         _lib.check(h.mmx_dense_rank(Q.data_ptr(), nq, G.data_ptr(), ng, d, gt_off.data_ptr(), gt_idx.data_ptr(), g_base,
                                     MODE_THRESHOLD, thr.data_ptr(), None, None, 0, None, 0, ws.data_ptr(), need.value,
                                     _stream()))
-    if not threshold_only:
+    top_s = top_i = None
+    if not threshold_only and top_k is not None and not want_scores:
+        need = ctypes.c_size_t()
+        _lib.check(h.mmx_dense_topk_workspace_bytes(nq, ng, ctypes.byref(need)))
+        ws = torch.empty(need.value, dtype=torch.uint8, device=Q.device)
+        top_s = torch.empty((nq, top_k), dtype=torch.float32, device=Q.device)
+        top_i = torch.empty((nq, top_k), dtype=torch.int32, device=Q.device)
+        _lib.check(h.mmx_dense_rank_topk(Q.data_ptr(), nq, G.data_ptr(), ng, d, gt_off.data_ptr(), gt_idx.data_ptr(),
+                                         g_base, thr.data_ptr(), cnt.data_ptr(), _ptr(bits), wpr, top_k, top_s.data_ptr(),
+                                         top_i.data_ptr(), ws.data_ptr(), need.value, _stream()))
+    elif not threshold_only:
         _lib.check(h.mmx_dense_rank(Q.data_ptr(), nq, G.data_ptr(), ng, d, gt_off.data_ptr(), gt_idx.data_ptr(), g_base,
                                     MODE_COUNT, thr.data_ptr(), cnt.data_ptr(), _ptr(bits), wpr, _ptr(scores),
                                     ng if want_scores else 0, None, 0, _stream()))
-    return ProtocolRanks(thr=thr, cnt_above=cnt, bits=bits, n_cols=ng, scores=scores)
+        if top_k is not None:
+            top_s, top_i = topk_from_scores(scores, top_k, g_base)
+    return ProtocolRanks(thr=thr, cnt_above=cnt, bits=bits, n_cols=ng, scores=scores, top_s=top_s, top_i=top_i)
 
 
 def dense_scores(Q: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
