@@ -38,6 +38,15 @@ WORKLOAD = ("ColPali-v1.3 MaxSim: 25000 queries x 20 tokens vs 5000 docs x 1030 
 METRIC = "maxsim_query_doc_pairs_per_s"
 
 
+def workload_config(world: int) -> dict:
+    """`config` of the JSON line — the same dict for both arms (the reference arm adds its bounded sample under
+    `cpu_baseline.sample`)."""
+    return {"workload": WORKLOAD, "n_queries": NQ, "n_docs": ND, "query_tokens": LQ, "doc_patches": LD,
+            "dim": DIM, "bootstrap_iterations": N_ITER, "ci_resamples": N_CI,
+            "parallelism": f"doc-shard x{world}" if world > 1 else "single GPU",
+            "l2": "inputs_exceed_l2 (1.32 GB of doc patches streamed per step; L2 is 126 MB)"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,7 +192,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": workload_config(int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -328,10 +337,7 @@ def run_ours(args):
         "metric": METRIC, "value": total_pairs / (ms_per_step * 1e-3), "unit": "pairs/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "n_queries": NQ, "n_docs": ND, "query_tokens": LQ, "doc_patches": LD,
-                   "dim": DIM, "bootstrap_iterations": N_ITER, "ci_resamples": N_CI,
-                   "parallelism": f"doc-shard x{world}" if world > 1 else "single GPU",
-                   "l2": "inputs_exceed_l2 (1.32 GB of doc patches streamed per step; L2 is 126 MB)"},
+        "config": workload_config(world),
         "e2e": {"value": total_pairs / e2e_s, "unit": "pairs/s", "ms_per_step": 1e3 * e2e_s,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "note": "mmx.run_retrieval_bootstrap from pinned host buffers; the reference's numpy MT19937 draws "

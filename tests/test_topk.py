@@ -87,6 +87,31 @@ def test_dense_topk_without_matrix(mmx_mod, nq, ng, d):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("nq,ng,d", [(300, 1500, 768), (513, 5000, 1152), (130, 40000, 256)])
+def test_rank_and_topk_in_one_call(mmx_mod, nq, ng, d):
+    """mmx_dense_rank_topk: the ranking COUNT pass stores the group maxima on its way, so thresholds, counts, bitmask
+    AND the top-k lists come out of one call — every output bit-identical to the separate calls (small gallery,
+    32-column groups, 256-column groups; shard offset g_base; ragged GT sets)."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(nq + 1)
+    G = unit(torch.randn(ng, d, generator=g)).bfloat16().to(dev)
+    gt = torch.randint(0, ng, (nq,), generator=g)
+    Q = unit(G[gt.to(dev)].float().cpu() + 2.0 * unit(torch.randn(nq, d, generator=g))).bfloat16().to(dev)
+    n_gt = torch.randint(1, 4, (nq,), generator=g)                      # 1..3 GT columns per query
+    off = torch.zeros(nq + 1, dtype=torch.int32)
+    off[1:] = torch.cumsum(n_gt, 0)
+    idx = torch.cat([(gt[i] + torch.arange(n_gt[i])) % ng for i in range(nq)]).int() + 64
+    off, idx = off.to(dev), idx.to(dev)
+    for k in (1, 10):
+        sep = mmx_mod.ops.dense_rank(Q, G, off, idx, g_base=64)
+        ts, ti = mmx_mod.ops.dense_topk(Q, G, k, g_base=64)
+        one = mmx_mod.ops.dense_rank(Q, G, off, idx, g_base=64, top_k=k)
+        assert torch.equal(one.thr, sep.thr) and torch.equal(one.cnt_above, sep.cnt_above)
+        assert torch.equal(one.bits, sep.bits)
+        assert torch.equal(one.top_s, ts) and torch.equal(one.top_i, ti)
+
+
+@pytest.mark.gpu
 def test_dense_topk_mass_ties_take_the_exact_fallback(mmx_mod):
     """200 identical gallery rows tie at the top: the 64-slot candidate list overflows and the row is recomputed exactly;
     ties resolve by column index."""
