@@ -197,7 +197,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -363,7 +363,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         line["maxsim_i2t"] = i2t_section(dev, K, W)
         line["dense"] = dense_section(dev, K, W, cpu_iters=0 if args.no_cpu_baseline else 2)
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -485,8 +485,19 @@ def dense_section(dev, K, W, cpu_iters=2):
             "I2T_R@1": [row["I2T_R@1_mean"], row["I2T_R@1_lower"], row["I2T_R@1_upper"]]}
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's original stdout."""
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 if __name__ == "__main__":
     a = parse_args()
+    # stdout carries the JSON line and nothing else: native libraries that write to file descriptor 1 (NCCL prints
+    # "NCCL version ..." there on the GPU boxes) are sent to stderr for the rest of the process
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -137,6 +137,27 @@ int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_above, cons
                     int64_t words_per_row, const int32_t* col2unit, const int32_t* q_unit, const uint8_t* mult, int B,
                     int64_t n_units, int64_t nq, int32_t* correct, int32_t* q_hits1, cudaStream_t stream);
 
+/* LIST mode — K1 + K3 for galleries whose [nq, ng] above-GT bitmask does not fit in memory (10^6 x 10^6
+ * would be 125 GB of bits). Same identity as above; the above-GT set of a query is kept as a list of at most `cap`
+ * columns, which is all K3 ever reads for queries with cnt_above <= cap and enough for min(c_q, 10) otherwise
+ * whenever the listed multiplicities already reach 10.
+ * mmx_dense_rank_lists: the COUNT pass of mmx_dense_rank (thr = merged thresholds, input) with cnt_above int32 [nq]
+ *                   (exact strict-greater count) and, instead of bits, list_i int32 [nq, cap] global column ids of the
+ *                   first hits to arrive + list_n int32 [nq] cursor (valid entries = min(list_n, cap)). Both zeroed here.
+ * mmx_lists_to_units: per-shard lists [n_shards, nq, cap] + cursors [n_shards, nq] (one all-gather when sharded)
+ *                   -> list_t [L, nq] transposed unit lists (col2unit nullable = identity), avail int32 [nq].
+ * mmx_boot_counts_lists: K3 on those lists. (iteration, query) pairs whose truncated list ran out below a multiplicity
+ *                   of 10 are left OUT of `correct` and reported as int32 pairs in unres [unres_cap, 2]; *unres_n counts
+ *                   them all (call again with more room if it exceeds unres_cap). The caller recounts them from the
+ *                   scores (api._resolve_unlisted); with cap = 64 the probability of one is ~1e-17 per pair. */
+int mmx_dense_rank_lists(const void* Q, int64_t nq, const void* G, int64_t ng, int d, int64_t g_base, const float* thr,
+                         int32_t* cnt_above, int32_t* list_i, int32_t* list_n, int cap, cudaStream_t stream);
+int mmx_lists_to_units(const int32_t* list_i, const int32_t* list_n, int n_shards, int64_t nq, int cap,
+                       const int32_t* col2unit, int L, int32_t* list_t, int32_t* avail, cudaStream_t stream);
+int mmx_boot_counts_lists(const int32_t* list_t, int L, const int32_t* cnt_above, const int32_t* q_unit,
+                          const uint8_t* mult, int B, int64_t n_units, int64_t nq, int32_t* correct, int32_t* q_hits1,
+                          int32_t* unres, int32_t* unres_n, int unres_cap, cudaStream_t stream);
+
 /* K4  CI resample means — replaces the 10 000 x (np.random.choice(data, n) ; np.mean) loop of main.py:268-270.
  * idx int32 [R, n] is the reference's index stream (RandomState.randint(0, n, (R, n)) == R x choice);
  * means[r] = np.mean(data[idx[r]]) bit for bit (fp64, numpy's pairwise summation order). */

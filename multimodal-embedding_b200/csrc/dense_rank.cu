@@ -187,8 +187,13 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             // per-row state, loaded while the MMAs of this tile are still running
             float thr = INFINITY;
             int e0 = 0, e1 = 0;
+            // candidate / above-GT list emission: a row whose counter had already passed the capacity when this tile
+            // started appends nothing more (rows far below their threshold would otherwise pay one atomic per hit);
+            // the counter still ends above the capacity, which is how the top-k path recognises an overflowed row
+            bool emit = false;
             if (MODE == MMX_MODE_COUNT) {
                 if (valid_row) thr = __ldg(p.thr + q);
+                emit = p.cand_n != nullptr && valid_row && __ldcg(p.cand_n + q) <= p.cand_cap;
             } else if (MODE == MMX_MODE_THRESHOLD && valid_row) {
                 e0 = __ldg(p.gt_off + q);
                 e1 = __ldg(p.gt_off + q + 1);
@@ -241,13 +246,13 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     const long long w = (c0 >> 5);
                     if (p.above_bits != nullptr && valid_row && w < p.words_per_row)
                         p.above_bits[q * p.words_per_row + w] = bits;
-                    if (p.cand_n != nullptr && bits != 0u && valid_row) {   // rare: a handful of hits per row in total
+                    if (emit && bits != 0u) {   // a handful of hits per row (top-k bar), or a row whose list is not full yet
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if ((bits >> j) & 1u) {
                                 const int slot = atomicAdd(p.cand_n + q, 1);
                                 if (slot < p.cand_cap) {
-                                    p.cand_s[q * p.cand_cap + slot] = __uint_as_float(v[j]);
+                                    if (p.cand_s != nullptr) p.cand_s[q * p.cand_cap + slot] = __uint_as_float(v[j]);
                                     p.cand_i[q * p.cand_cap + slot] = (int32_t)(p.g_base + c0 + j);
                                 }
                             }
@@ -631,4 +636,37 @@ extern "C" int mmx_dense_rank_topk(const void* Q, int64_t nq, const void* G, int
     p.grp_tile = t.grp_tile;
     if (int rc = launch_dense(Q, nq, G, ng, d, p, stream)) return rc;
     return topk_from_group_maxima(Q, nq, G, ng, d, g_base, k, top_s, top_i, ws, t, stream);
+}
+
+
+// K1 in LIST mode, for galleries whose [nq, ng] above-GT bitmask does not fit in memory (a 10^6 x 10^6
+// problem would need 125 GB of bits): the COUNT pass appends the columns that score above the threshold to a per-query
+// list of `cap` entries (global column ids; whichever hits arrive first, a full list takes no more) next to the exact
+// count. The bootstrap only needs min(c_q, 10) with c_q = sum of the drawn multiplicities over the above-GT set, so
+// a list that holds the WHOLE set (cnt_above <= cap) is exact, and a truncated one is exact whenever its own
+// multiplicities already reach 10 (mmx_boot_counts_lists reports the other cases for an exact recount).
+// thr = merged thresholds (input); cnt_above [nq] and list_n [nq] are zeroed here.
+extern "C" int mmx_dense_rank_lists(const void* Q, int64_t nq, const void* G, int64_t ng, int d, int64_t g_base,
+                                    const float* thr, int32_t* cnt_above, int32_t* list_i, int32_t* list_n, int cap,
+                                    cudaStream_t stream) {
+    MMX_REQUIRE(nq >= 0 && ng >= 0 && d >= 8 && d % 8 == 0, "bad shape nq=%lld ng=%lld d=%d (d must be a multiple of 8)",
+                (long long)nq, (long long)ng, d);
+    MMX_REQUIRE(thr != nullptr && cnt_above != nullptr && list_i != nullptr && list_n != nullptr, "NULL argument");
+    MMX_REQUIRE(cap >= 1 && cap <= 1024, "cap out of range");
+    MMX_REQUIRE(g_base + ng < (1ll << 31), "column index does not fit int32");
+    if (nq == 0) return 0;
+    if (mmx_device_check() != 0) return -3;
+    MMX_CHECK_CUDA(cudaMemsetAsync(cnt_above, 0, (size_t)nq * 4, stream));
+    MMX_CHECK_CUDA(cudaMemsetAsync(list_n, 0, (size_t)nq * 4, stream));
+    if (ng == 0) return 0;
+    Params p;
+    if (base_params(p, nq, ng, d) != 0) return -2;
+    p.g_base = g_base;
+    p.thr = const_cast<float*>(thr);
+    p.cnt_above = cnt_above;
+    p.cand_i = list_i;
+    p.cand_n = list_n;
+    p.cand_cap = cap;
+    p.mode = MMX_MODE_COUNT;
+    return launch_dense(Q, nq, G, ng, d, p, stream);
 }

@@ -62,12 +62,34 @@ __global__ void above_lists_kernel(const uint32_t* __restrict__ bits, long long 
     }
 }
 
+// LIST mode (K1 mmx_dense_rank_lists): per-shard column lists [n_shards, nq, cap] + cursors [n_shards, nq] ->
+// list_t[i * nq + q] = unit of the i-th entry of query q's concatenated lists (shard order), i < L; total[q] = number
+// of entries available (sum of min(cursor, cap) over shards, unclamped by L).
+__global__ void lists_to_units_kernel(const int32_t* __restrict__ list_i, const int32_t* __restrict__ list_n,
+                                      int n_shards, long long nq, int cap, const int32_t* __restrict__ col2unit, int L,
+                                      int32_t* __restrict__ list_t, int32_t* __restrict__ avail) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    int pos = 0, tot = 0;
+    for (int s = 0; s < n_shards; ++s) {
+        const int n = min(list_n[(long long)s * nq + q], cap);
+        tot += n;
+        const int32_t* src = list_i + ((long long)s * nq + q) * cap;
+        for (int i = 0; i < n && pos < L; ++i, ++pos) {
+            const int32_t col = src[i];
+            list_t[(long long)pos * nq + q] = col2unit != nullptr ? col2unit[col] : col;
+        }
+    }
+    avail[q] = tot;
+}
+
 // One block per bootstrap iteration b. mult[b,:] (uint8, saturated) sits in shared memory when it fits.
 __global__ void __launch_bounds__(256)
 boot_counts_kernel(const int32_t* __restrict__ list_t, int L, const int32_t* __restrict__ cnt_above,
                    const uint32_t* __restrict__ bits, long long wpr, const int32_t* __restrict__ col2unit,
                    const int32_t* __restrict__ q_unit, const uint8_t* __restrict__ mult, long long n_units,
-                   long long nq, int mult_in_smem, int32_t* __restrict__ correct, int32_t* __restrict__ q_hits1) {
+                   long long nq, int mult_in_smem, int32_t* __restrict__ correct, int32_t* __restrict__ q_hits1,
+                   int32_t* __restrict__ unres, int32_t* __restrict__ unres_n, int unres_cap) {
     extern __shared__ uint8_t sm_mult[];
     __shared__ int red[3][8];
     const int b = blockIdx.x;
@@ -85,6 +107,16 @@ boot_counts_kernel(const int32_t* __restrict__ list_t, int L, const int32_t* __r
         const int len = min(cnt, L);
         int c = 0;
         for (int i = 0; i < len && c < 10; ++i) c += mrow[list_t[(long long)i * nq + q]];
+        if (c < 10 && cnt > L && bits == nullptr) {
+            // LIST mode: the truncated list ran out before saturating and there is no bitmask to fall back to: leave
+            // this (iteration, query) out of the sums and report it; the caller recounts it exactly from the scores
+            const int slot = atomicAdd(unres_n, 1);
+            if (slot < unres_cap) {
+                unres[2 * slot] = b;
+                unres[2 * slot + 1] = (int32_t)q;
+            }
+            continue;
+        }
         if (c < 10 && cnt > L) {
             // truncated list ran out before saturating: exact walk over the bitmask row (rare)
             c = 0;
@@ -231,6 +263,8 @@ gather_mean_kernel(const double* __restrict__ data, int n_data, const int32_t* _
 using namespace mmx;
 using namespace mmx::stats;
 
+static const char boot_tag = 0;  // boot_counts_kernel's shared-memory attribute: set once per device
+
 extern "C" int mmx_bincount(const int32_t* sample_idx, int B, int64_t n_draws, int64_t n_units, int32_t* scratch,
                             uint8_t* mult, cudaStream_t stream) {
     MMX_REQUIRE(B >= 0 && n_draws >= 0 && n_units > 0, "bad shape");
@@ -264,11 +298,41 @@ extern "C" int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_
     if (B == 0) return 0;
     const int in_smem = n_units <= 200 * 1024;
     const size_t smem = in_smem ? (size_t)((n_units + 15) & ~15ll) : 0;
-    static const char boot_tag = 0;
     if (smem > 48 * 1024 && first_use_on_device(&boot_tag))
         MMX_CHECK_CUDA(cudaFuncSetAttribute(boot_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
     boot_counts_kernel<<<B, 256, smem, stream>>>(list_t, L, cnt_above, above_bits, words_per_row, col2unit, q_unit, mult,
-                                                 n_units, nq, in_smem, correct, q_hits1);
+                                                 n_units, nq, in_smem, correct, q_hits1, nullptr, nullptr, 0);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mmx_lists_to_units(const int32_t* list_i, const int32_t* list_n, int n_shards, int64_t nq, int cap,
+                                  const int32_t* col2unit, int L, int32_t* list_t, int32_t* avail, cudaStream_t stream) {
+    MMX_REQUIRE(list_i && list_n && list_t && avail, "NULL argument");
+    MMX_REQUIRE(n_shards >= 1 && cap >= 1 && L >= 1 && L <= 1024, "bad list geometry");
+    if (nq == 0) return 0;
+    lists_to_units_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(list_i, list_n, n_shards, nq, cap, col2unit,
+                                                                           L, list_t, avail);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// K3 without a bitmask (LIST mode). list_t holds min(cnt_above[q], L) units of query q's above-GT set — all of it
+// when cnt_above[q] <= L. (iteration, query) pairs whose truncated list did not reach a multiplicity of 10 are left
+// out of `correct` and reported in unres [unres_cap, 2] / *unres_n (may exceed unres_cap: call again with more room).
+extern "C" int mmx_boot_counts_lists(const int32_t* list_t, int L, const int32_t* cnt_above, const int32_t* q_unit,
+                                     const uint8_t* mult, int B, int64_t n_units, int64_t nq, int32_t* correct,
+                                     int32_t* q_hits1, int32_t* unres, int32_t* unres_n, int unres_cap,
+                                     cudaStream_t stream) {
+    MMX_REQUIRE(list_t && cnt_above && mult && correct && unres && unres_n && unres_cap >= 1, "NULL argument");
+    MMX_CHECK_CUDA(cudaMemsetAsync(unres_n, 0, sizeof(int32_t), stream));
+    if (B == 0) return 0;
+    const int in_smem = n_units <= 200 * 1024;
+    const size_t smem = in_smem ? (size_t)((n_units + 15) & ~15ll) : 0;
+    if (smem > 48 * 1024 && first_use_on_device(&boot_tag))
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(boot_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
+    boot_counts_kernel<<<B, 256, smem, stream>>>(list_t, L, cnt_above, nullptr, 0, nullptr, q_unit, mult, n_units, nq,
+                                                 in_smem, correct, q_hits1, unres, unres_n, unres_cap);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
