@@ -16,20 +16,25 @@ docs, queries = synth_colpali(333, 333 * 5, q_len=(6, 14), sigma_q=2.5, seed=12,
 docs[17] = -docs[17].abs(); queries[85] = queries[85].abs()      # a padded document whose zero row wins a maximum
 q2d = np.arange(333 * 5) // 5
 img, all_txt = synth_dense(2000, 256, 4.0, seed=3)
-cases = {"colpali": (queries, docs, q2d, {"type": "colpali", "name": "c"}),
-         "dense": (all_txt, img, np.arange(10000) // 5, {"type": "dense", "name": "d"})}
+cases = {"colpali": (queries, docs, q2d, {"type": "colpali", "name": "c"}, {}),
+         "dense": (all_txt, img, np.arange(10000) // 5, {"type": "dense", "name": "d"}, {}),
+         # LIST mode (no bitmask) with a starved capacity: the sharded exact recount must give the bitmask result
+         "dense_lists_cap3": (all_txt, img, np.arange(10000) // 5, {"type": "dense", "name": "d"}, {"list_mode": True, "list_cap": 3}),
+         "dense_lists_cap64": (all_txt, img, np.arange(10000) // 5, {"type": "dense", "name": "d"}, {"list_mode": True})}
 ref_path = Path(os.environ.get("TMPDIR", "/tmp")) / "mmx_sharded_ref.pkl"
 if rank == 0:
-    ref = {k: mmx.run_retrieval_bootstrap(q, d, g, mi, 200, rng=np.random.RandomState(9)) for k, (q, d, g, mi) in cases.items()}
+    ref = {k: mmx.run_retrieval_bootstrap(q, d, g, mi, 200, rng=np.random.RandomState(9)) for k, (q, d, g, mi, _) in cases.items()}
     ref_path.write_bytes(pickle.dumps(ref))
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ok = True
-for k, (q, d, g, mi) in cases.items():
+for k, (q, d, g, mi, kw) in cases.items():
     a, b = mmx.sharded.shard_bounds(len(d), world)[rank]
     shard = d[a:b]
-    res = mmx.run_retrieval_bootstrap(q, shard, g, mi, 200, rng=np.random.RandomState(9))
+    res = mmx.run_retrieval_bootstrap(q, shard, g, mi, 200, rng=np.random.RandomState(9), **kw)
     if rank == 0:
         ref = pickle.loads(ref_path.read_bytes())[k]
+        if kw:
+            print(k, res["_list_mode"], flush=True)
         for key in ref:
             same = np.array_equal(ref[key], res[key]) if isinstance(ref[key], np.ndarray) else ref[key] == res[key]
             if not same:

@@ -121,6 +121,19 @@ _SIGNATURES = {
         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64,  # col2unit, q_unit, mult, B, n_units
         _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,            # nq, correct, q_hits1, stream
     ]),
+    "mmx_dense_rank_lists": (_c.c_int, [
+        _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int64,   # Q, nq, G, ng, d, g_base
+        _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,  # thr, cnt_above, list_i, list_n, cap, stream
+    ]),
+    "mmx_lists_to_units": (_c.c_int, [
+        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int,     # list_i, list_n, n_shards, nq, cap
+        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,  # col2unit, L, list_t, avail, stream
+    ]),
+    "mmx_boot_counts_lists": (_c.c_int, [
+        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,  # list_t, L, cnt_above, q_unit, mult
+        _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p,    # B, n_units, nq, correct, q_hits1
+        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,               # unres, unres_n, unres_cap, stream
+    ]),
     "mmx_ci_means": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,   # data, n, idx, R, means, stream
     ]),

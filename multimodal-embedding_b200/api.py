@@ -568,8 +568,12 @@ def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device
     return S
 
 
+BITMASK_LIMIT_BYTES = 16 << 30     # above-GT bitmasks larger than this switch the dense path to LIST mode
+
+
 def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: Dict, n_iterations: int, rng=None,
-                            group=None, timings: Optional[Dict[str, float]] = None) -> Optional[Dict[str, Any]]:
+                            group=None, timings: Optional[Dict[str, float]] = None, list_mode: Optional[bool] = None,
+                            list_cap: Optional[int] = None) -> Optional[Dict[str, Any]]:
     """One retrieval protocol (T2I-style: every query has one ground-truth document) scored, ranked, bootstrapped and
     aggregated like main.py:586-651 — for the configurations whose query set is not "caption 0 of every image"
     (BASELINE.json configs 4-5: 25 000 caption queries against 5 000 / 100 000 documents).
@@ -578,7 +582,12 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     is the document: an iteration draws ``choice(n_docs, n_docs)`` documents, each draw brings along its queries.
     With a torch.distributed ``group`` (world > 1) every rank passes ITS contiguous shard of the documents
     (``sharded.shard_bounds``) and all queries; rank 0 returns the result, the others None.
-    numpy stream: n_iterations x choice(n_docs, n_docs), then 3 x 10 000 x choice(values, n_iterations)."""
+    numpy stream: n_iterations x choice(n_docs, n_docs), then 3 x 10 000 x choice(values, n_iterations).
+
+    Dense galleries whose [n_queries, n_docs] above-GT bitmask would exceed BITMASK_LIMIT_BYTES (a 10^6 x 10^6 problem
+    needs 125 GB of bits) run in LIST mode (``list_mode`` forces it either way): K1 keeps at most
+    ``list_cap`` above-GT columns per query and shard next to the exact count, K3 walks those lists, and the pairs
+    a truncated list cannot settle are recounted exactly from the scores — same integers as the bitmask path."""
     import torch.distributed as dist
     from . import sharded
     dev = _device()
@@ -646,19 +655,39 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
                          torch.int32)
     marks.append(("score_queued", time.perf_counter()))
     thr = sharded.merge_thresholds(local.thr, group)
+    if list_mode is None:
+        list_mode = (not colpali) and nq * n_docs // 8 > BITMASK_LIMIT_BYTES
+    if list_mode and colpali:
+        raise ValueError("LIST mode applies to the dense path (the MaxSim path materialises its score matrix)")
     if colpali:
         local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, thr=thr)
+    elif list_mode:
+        local = ops.dense_rank_lists(Q, G, gt_off, gt_idx, g_base=g_base, thr=thr, cap=list_cap or ops.LIST_CAP)
+        recount = ops.dense_unlisted_resolver(Q, G, thr, None, g_base)        # this shard's share of an exact recount
     else:
         local = ops.dense_rank(Q, G, gt_off, gt_idx, g_base=g_base, thr=thr)
     ranks = sharded.merge_ranks(local, bounds, group)
     if rank != 0:
+        if list_mode:
+            sharded.unlisted_round(recount, None, None, group)               # serve rank 0's recount, if there is one
         return None
     ranks.q_unit = gt_idx
     if DEVICE_RNG:
         torch.cuda.current_stream().wait_event(rng_done)
     mult = ops.bincount(sample_indices, n_docs)
-    correct = ops.boot_counts(ranks, mult)                                                       # [B, 3] int32
-    denom = mult.to(torch.float64)[:, gt_idx.long()].sum(dim=1)          # query copies drawn in each iteration
+    if list_mode:
+        rounds, k3_stats = [], {}
+
+        def resolve(pairs, mult_rows):
+            rounds.append(1)
+            return sharded.unlisted_round(recount, pairs, mult_rows, group)
+        correct = ops.boot_counts_lists(ranks, mult, resolve, stats=k3_stats)                    # [B, 3] int32
+        if not rounds:
+            sharded.unlisted_round(recount, None, None, group)               # nothing unsettled: release the other ranks
+    else:
+        correct = ops.boot_counts(ranks, mult)                                                   # [B, 3] int32
+    # query copies drawn in each iteration (integer sum: the same doubles as summing float64 copies)
+    denom = mult[:, gt_idx.long()].sum(dim=1, dtype=torch.int64).to(torch.float64)
     values = 100.0 * correct.to(torch.float64) / denom[:, None]                                  # main.py:358
     means = ops.ci_means_batched(values.t().contiguous(), ci_idx)                                # three CIs, one launch
     marks.append(("stats_queued", time.perf_counter()))
@@ -677,6 +706,9 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         out[f"R@{k}_std"] = np.std(v)
     out["base"] = ranks.recall()
     out["_bootstrap_values"] = values_h
+    if list_mode:
+        out["_list_mode"] = {"cap": int(ranks.list_i.shape[2]), "shards": int(ranks.list_i.shape[0]),
+                             "unresolved_pairs": k3_stats.get("unresolved_pairs", 0)}
     if timings is not None:
         timings["score_ms"] = ev[0].elapsed_time(ev[1])
         marks.append(("return", time.perf_counter()))

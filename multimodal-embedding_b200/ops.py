@@ -15,6 +15,8 @@ from . import _lib
 
 MODE_THRESHOLD, MODE_COUNT = 0, 1
 LIST_LEN = 32          # entries kept per above-GT list (rows with more fall back to the exact bitmask walk)
+LIST_CAP = 64          # LIST mode (no bitmask): entries kept per query and shard; P(64 draws of Poisson(1) sum < 10) ~ 1e-17
+UNRESOLVED_CAP = 1 << 16
 
 
 def _stream() -> int:
@@ -56,6 +58,10 @@ class ProtocolRanks:
     ties: Optional[torch.Tensor] = None       # [nq] int32 non-GT columns scoring EXACTLY the threshold (tie class T2)
     top_s: Optional[torch.Tensor] = None      # [nq, k] fp32 top-k scores (KT), higher first, ties by lower column
     top_i: Optional[torch.Tensor] = None      # [nq, k] int32 global column ids, -1 = padding
+    # LIST mode (galleries whose bitmask does not fit): bits is None and the above-GT sets are kept as
+    # per-shard column lists [n_shards, nq, cap] (global ids, first arrivals) with cursors [n_shards, nq]
+    list_i: Optional[torch.Tensor] = None
+    list_n: Optional[torch.Tensor] = None
 
     @property
     def nq(self) -> int:
@@ -164,6 +170,59 @@ def dense_rank(Q: torch.Tensor, G: torch.Tensor, gt_off: torch.Tensor, gt_idx: t
         if top_k is not None:
             top_s, top_i = topk_from_scores(scores, top_k, g_base)
     return ProtocolRanks(thr=thr, cnt_above=cnt, bits=bits, n_cols=ng, scores=scores, top_s=top_s, top_i=top_i)
+
+
+def dense_rank_lists(Q: torch.Tensor, G: torch.Tensor, gt_off: torch.Tensor, gt_idx: torch.Tensor, g_base: int = 0,
+                     thr: Optional[torch.Tensor] = None, cap: int = LIST_CAP) -> ProtocolRanks:
+    """K1 in LIST mode: thresholds (unless given: shard-merged), exact counts, and per query the first `cap` columns
+    to score above the threshold instead of the [nq, ng] bitmask — for galleries where nq * ng bits do not fit."""
+    if thr is None:
+        thr = dense_rank(Q, G, gt_off, gt_idx, want_bits=False, g_base=g_base, threshold_only=True).thr
+    _need_cuda(Q, G, thr)
+    if Q.dtype != torch.bfloat16 or G.dtype != torch.bfloat16:
+        raise TypeError("dense rank kernel takes bf16 embeddings")
+    Q, G = Q.contiguous(), G.contiguous()
+    nq, d = Q.shape
+    ng = G.shape[0]
+    cnt = torch.empty((nq,), dtype=torch.int32, device=Q.device)
+    list_i = torch.empty((1, nq, cap), dtype=torch.int32, device=Q.device)
+    list_n = torch.empty((1, nq), dtype=torch.int32, device=Q.device)
+    _lib.check(_lib.lib().mmx_dense_rank_lists(Q.data_ptr(), nq, G.data_ptr(), ng, d, g_base, thr.data_ptr(),
+                                               cnt.data_ptr(), list_i.data_ptr(), list_n.data_ptr(), cap, _stream()))
+    return ProtocolRanks(thr=thr, cnt_above=cnt, bits=None, n_cols=ng, list_i=list_i, list_n=list_n)
+
+
+def dense_unlisted_resolver(Q: torch.Tensor, G: torch.Tensor, thr: torch.Tensor,
+                            col2unit: Optional[torch.Tensor] = None, g_base: int = 0):
+    """Exact recount for the (iteration, query) pairs LIST-mode K3 could not settle from a truncated list. Returns
+    ``resolve(pairs[n, 2], mult_rows[r, n_units]) -> c int64 [n]`` with pairs[:, 0] an index into mult_rows and
+    c = sum over THIS shard's columns of mult_rows[b, unit(col)] * [S[q, col] > thr[q]] — the scores come from K1's own
+    MMA path (a few materialised rows at a time), so the comparison is the one the COUNT pass made. Partial sums of
+    gallery shards add (sharded.unlisted_round)."""
+    ng = G.shape[0]
+    cols = torch.arange(g_base, g_base + ng, device=G.device)
+    units = cols if col2unit is None else col2unit[cols].long()
+
+    def resolve(pairs: torch.Tensor, mult_rows: torch.Tensor) -> torch.Tensor:
+        c = torch.zeros(pairs.shape[0], dtype=torch.int64, device=G.device)
+        if ng == 0 or pairs.shape[0] == 0:
+            return c
+        order = torch.argsort(pairs[:, 1], stable=True)
+        q_sorted = pairs[order, 1].long().contiguous()
+        qs = torch.unique(q_sorted)
+        rows_per_block = max(1, min(64, (256 << 20) // (4 * ng)))
+        for i in range(0, qs.numel(), rows_per_block):
+            blk = qs[i:i + rows_per_block]
+            above = dense_scores(Q[blk].contiguous(), G) > thr[blk][:, None]             # [rows, ng]
+            lo = int(torch.searchsorted(q_sorted, blk[0]).item())
+            hi = int(torch.searchsorted(q_sorted, blk[-1], right=True).item())
+            for j in range(lo, hi, 64):
+                sel = order[j:min(j + 64, hi)]
+                row_of = torch.searchsorted(blk, pairs[sel, 1].long())
+                m = mult_rows[pairs[sel, 0].long()][:, units]                             # [n, ng] uint8
+                c[sel] = (m * above[row_of]).sum(dim=1, dtype=torch.int64)
+        return c
+    return resolve
 
 
 def dense_scores(Q: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
@@ -318,6 +377,8 @@ def bincount(sample_idx: torch.Tensor, n_units: int) -> torch.Tensor:
 def boot_counts(r: ProtocolRanks, mult: torch.Tensor, list_len: int = LIST_LEN,
                 q_hits1: Optional[torch.Tensor] = None) -> torch.Tensor:
     """K3 for one protocol: mult uint8 CUDA [B, n_units] -> int32 CUDA [B, 3] correct counts for k = 1, 5, 10."""
+    if r.bits is None and r.list_i is not None:
+        raise ValueError("LIST-mode ranks: use boot_counts_lists (it needs the exact-recount callback)")
     _need_cuda(mult, r.bits)
     if r.bits is None:
         raise ValueError("bootstrap needs the above-GT bitmask (want_bits=True)")
@@ -330,6 +391,53 @@ def boot_counts(r: ProtocolRanks, mult: torch.Tensor, list_len: int = LIST_LEN,
     _lib.check(h.mmx_boot_counts(list_t.data_ptr(), list_len, r.cnt_above.data_ptr(), r.bits.data_ptr(), wpr,
                                  _ptr(r.col2unit), _ptr(r.q_unit), mult.data_ptr(), B, n_units, nq, correct.data_ptr(),
                                  _ptr(q_hits1), _stream()))
+    return correct
+
+
+def boot_counts_lists(r: ProtocolRanks, mult: torch.Tensor, resolve, q_hits1: Optional[torch.Tensor] = None,
+                      list_len: Optional[int] = None, stats: Optional[dict] = None) -> torch.Tensor:
+    """K3 in LIST mode: `r` from dense_rank_lists (per-shard lists stacked along dim 0 after the all-gather, cnt_above
+    = the shard-summed exact counts). Pairs the truncated lists cannot settle are recounted exactly through
+    `resolve(pairs[n, 2], mult_rows) -> c[n]` (dense_unlisted_resolver; sharded.unlisted_round across gallery shards)
+    and added back: the result equals the bitmask path bit for bit."""
+    _need_cuda(mult, r.list_i, r.list_n, r.cnt_above)
+    n_shards, nq, cap = r.list_i.shape
+    L = cap if list_len is None else min(list_len, cap)
+    B, n_units = mult.shape
+    h = _lib.lib()
+    dev = mult.device
+    list_t = torch.empty((L, nq), dtype=torch.int32, device=dev)
+    avail = torch.empty((nq,), dtype=torch.int32, device=dev)
+    _lib.check(h.mmx_lists_to_units(r.list_i.data_ptr(), r.list_n.data_ptr(), n_shards, nq, cap, _ptr(r.col2unit), L,
+                                    list_t.data_ptr(), avail.data_ptr(), _stream()))
+    correct = torch.empty((B, 3), dtype=torch.int32, device=dev)
+    unres_cap = UNRESOLVED_CAP
+    while True:
+        unres = torch.empty((unres_cap, 2), dtype=torch.int32, device=dev)
+        unres_n = torch.empty((1,), dtype=torch.int32, device=dev)
+        hits = None if q_hits1 is None else q_hits1.clone()
+        _lib.check(h.mmx_boot_counts_lists(list_t.data_ptr(), L, r.cnt_above.data_ptr(), _ptr(r.q_unit), mult.data_ptr(),
+                                           B, n_units, nq, correct.data_ptr(), _ptr(hits), unres.data_ptr(),
+                                           unres_n.data_ptr(), unres_cap, _stream()))
+        n_un = int(unres_n.item())
+        if n_un <= unres_cap:
+            break
+        unres_cap = n_un                                  # more unsettled pairs than room: run again with enough
+    if q_hits1 is not None:
+        q_hits1.copy_(hits)
+    if stats is not None:
+        stats["unresolved_pairs"] = n_un
+    if n_un:
+        pairs = unres[:n_un]
+        b_used, b_pos = torch.unique(pairs[:, 0], return_inverse=True)     # only these iterations' multiplicity rows travel
+        c = resolve(torch.stack([b_pos.to(torch.int32), pairs[:, 1]], dim=1), mult[b_used.long()].contiguous())
+        b, q = pairs[:, 0].long(), pairs[:, 1].long()
+        mq = mult[b, q if r.q_unit is None else r.q_unit[q].long()].long()
+        for col, k in enumerate((1, 5, 10)):
+            add = torch.minimum(mq, (k - c).clamp_min(0))
+            correct[:, col] += torch.zeros(B, dtype=torch.int64, device=dev).index_add_(0, b, add).to(torch.int32)
+            if k == 1 and q_hits1 is not None:
+                q_hits1 += torch.zeros(nq, dtype=torch.int64, device=dev).index_add_(0, q, add).to(q_hits1.dtype)
     return correct
 
 

@@ -2,7 +2,8 @@
 gallery columns split into contiguous balanced shards, exactly two tiny collectives per scoring pass:
 
   1. all-reduce(MAX) of the per-query GT thresholds (the GT column of a query lives on one shard only);
-  2. all-reduce(SUM) of the strict-greater counts + all-gather of each shard's bitmask columns.
+  2. all-reduce(SUM) of the strict-greater counts + all-gather of each shard's bitmask columns (or, in LIST mode for
+     galleries whose bitmask does not fit, of each shard's truncated above-GT column list).
 When the retrieved items themselves are wanted, ONE all-gather of a fixed-size record per query — the shard's top-k
 scores and global column ids, 8k bytes — followed by a local merge (mmx_merge_topk) gives the global top-k.
 
@@ -62,8 +63,49 @@ def merge_ranks(local: ProtocolRanks, bounds: List[Tuple[int, int]], group=None)
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine, group=group)
         bits = place_bit_columns(parts, bounds)
+    list_i = list_n = None
+    if local.list_i is not None:
+        # LIST mode: ONE all-gather of a fixed-size record per query — the shard's `cap` column ids and its cursor
+        cap = local.list_i.shape[2]
+        rec = torch.cat([local.list_i[0], local.list_n[0][:, None]], dim=1).contiguous()      # [nq, cap + 1]
+        parts = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(parts, rec, group=group)
+        list_i = torch.stack([p[:, :cap] for p in parts]).contiguous()
+        list_n = torch.stack([p[:, cap] for p in parts]).contiguous()
     return ProtocolRanks(thr=local.thr, cnt_above=cnt, bits=bits, n_cols=bounds[-1][1], col2unit=local.col2unit,
-                         q_unit=local.q_unit)
+                         q_unit=local.q_unit, list_i=list_i, list_n=list_n)
+
+
+def unlisted_round(local_resolve, pairs, mult_rows, group=None) -> torch.Tensor:
+    """The exact recount of LIST-mode K3's unsettled (iteration, query) pairs across gallery shards. Rank 0 (which ran
+    K3) passes the pairs and the multiplicity rows they refer to, every other rank None; EVERY rank calls this once
+    per K3 call (rank 0 with pairs=None when nothing was left unsettled). The pairs and rows are broadcast, each
+    rank recounts over its own columns (ops.dense_unlisted_resolver) and the partial sums are all-reduced."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local_resolve(pairs, mult_rows) if pairs is not None else None
+    rank = dist.get_rank(group)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dev = mult_rows.device if mult_rows is not None else _group_device(group)
+    head = torch.zeros(3, dtype=torch.int64, device=dev)
+    if rank == 0 and pairs is not None:
+        head = torch.tensor([pairs.shape[0], mult_rows.shape[0], mult_rows.shape[1]], dtype=torch.int64, device=dev)
+    dist.broadcast(head, src=src, group=group)
+    n, r, u = (int(x) for x in head.tolist())
+    if n == 0:
+        return None
+    if rank != 0:
+        pairs = torch.empty((n, 2), dtype=torch.int32, device=dev)
+        mult_rows = torch.empty((r, u), dtype=torch.uint8, device=dev)
+    pairs, mult_rows = pairs.contiguous(), mult_rows.contiguous()
+    dist.broadcast(pairs, src=src, group=group)
+    dist.broadcast(mult_rows, src=src, group=group)
+    c = local_resolve(pairs, mult_rows)
+    dist.all_reduce(c, op=dist.ReduceOp.SUM, group=group)
+    return c
+
+
+def _group_device(group=None) -> torch.device:
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
 
 
 def place_bit_columns(parts: List[torch.Tensor], bounds: List[Tuple[int, int]]) -> torch.Tensor:

@@ -657,6 +657,65 @@ def test_run_retrieval_bootstrap_vs_oracle(mmx_mod, monkeypatch):
             assert res[k] == res2[k], k
 
 
+def test_dense_rank_lists_hold_the_above_gt_set(mmx_mod):
+    """K1 LIST mode: exact counts equal the bitmask pass; every listed column is a set bit, no column is
+    listed twice, min(count, cap) columns are listed — the whole set whenever it fits. Includes a shard offset and a
+    gallery that spans several 256-column tiles and both accumulator halves."""
+    dev = torch.device("cuda:0")
+    ops = mmx_mod.ops
+    for nq, ng, d, sigma, cap, g_base in ((700, 3000, 128, 6.0, 64, 0), (513, 9000, 64, 9.0, 16, 1000), (40, 300, 64, 4.0, 4, 7)):
+        img, all_txt = synth_dense(max(nq, ng), d, sigma, seed=nq)
+        G, Q = img[:ng].contiguous().to(dev), all_txt[0::5][:nq].contiguous().to(dev)
+        off = torch.arange(nq + 1, dtype=torch.int32, device=dev)
+        idx = (torch.arange(nq, dtype=torch.int32, device=dev) % ng) + g_base
+        ref = ops.dense_rank(Q, G, off, idx, g_base=g_base)
+        got = ops.dense_rank_lists(Q, G, off, idx, g_base=g_base, cap=cap)
+        assert got.bits is None and torch.equal(got.thr, ref.thr) and torch.equal(got.cnt_above, ref.cnt_above)
+        above = np.unpackbits(ref.bits.cpu().numpy().view(np.uint8), axis=1, bitorder="little")[:, :ng].astype(bool)
+        cnt, li, ln = ref.cnt_above.cpu().numpy(), got.list_i[0].cpu().numpy() - g_base, got.list_n[0].cpu().numpy()
+        assert (cnt > cap).any() and (cnt <= cap).any()                 # both regimes are exercised
+        for q in range(nq):
+            n = min(int(ln[q]), cap)
+            assert n == min(int(cnt[q]), cap) and (int(ln[q]) > cap) == (int(cnt[q]) > cap)
+            cols = li[q, :n]
+            assert above[q, cols].all() and len(set(cols.tolist())) == n
+
+
+def test_list_mode_bootstrap_equals_bitmask_mode(mmx_mod):
+    """run_retrieval_bootstrap on a dense gallery in LIST mode (galleries whose N^2 bitmask does not fit) returns the
+    same integers, CIs and generator state as the bitmask path — with a comfortable capacity (nothing unsettled) and
+    with a starved one that sends many (iteration, query) pairs through the exact recount."""
+    n_docs, per, d = 900, 2, 128
+    img, all_txt = synth_dense(n_docs, d, 7.0, seed=21)
+    queries = torch.cat([all_txt[0::5], all_txt[1::5]]).contiguous()     # 2 caption queries per document
+    q2d = np.concatenate([np.arange(n_docs), np.arange(n_docs)])
+    m_info = {"type": "dense", "name": "DenseSynth"}
+    B = 40
+    rs = np.random.RandomState(9)
+    ref = mmx_mod.run_retrieval_bootstrap(queries, img, q2d, m_info, B, rng=rs, list_mode=False)
+    after = rs.randint(0, 1 << 30)
+    assert "_list_mode" not in ref
+    for cap, expect_unsettled in ((64, False), (3, True)):
+        rs2 = np.random.RandomState(9)
+        got = mmx_mod.run_retrieval_bootstrap(queries, img, q2d, m_info, B, rng=rs2, list_mode=True, list_cap=cap)
+        assert got["_list_mode"]["cap"] == cap and (got["_list_mode"]["unresolved_pairs"] > 0) == expect_unsettled
+        assert np.array_equal(got["_bootstrap_values"], ref["_bootstrap_values"]) and got["base"] == ref["base"]
+        for k in (1, 5, 10):
+            for f in ("mean", "lower", "upper", "std"):
+                assert got[f"R@{k}_{f}"] == ref[f"R@{k}_{f}"]
+        assert rs2.randint(0, 1 << 30) == after
+    # the automatic switch: a bitmask over the limit takes LIST mode on its own
+    api = mmx_mod.api
+    old = api.BITMASK_LIMIT_BYTES
+    api.BITMASK_LIMIT_BYTES = 1000
+    try:
+        auto = mmx_mod.run_retrieval_bootstrap(queries, img, q2d, m_info, B, rng=np.random.RandomState(9))
+    finally:
+        api.BITMASK_LIMIT_BYTES = old
+    assert auto["_list_mode"]["cap"] == mmx_mod.ops.LIST_CAP
+    assert np.array_equal(auto["_bootstrap_values"], ref["_bootstrap_values"])
+
+
 def test_run_bootstrap_colpali_small(mmx_mod):
     """ColPali path end to end on a small ragged problem: base metrics and bootstrap integers vs the oracle."""
     n = 40

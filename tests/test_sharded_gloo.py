@@ -72,6 +72,63 @@ def test_sharded_merge_world2_gloo(tmp_path, n_cols):
     assert [Path(tmp_path, f"ok{r}").read_text() for r in range(world)] == ["1", "1"]
 
 
+def _worker_lists(rank, world, port, out_dir):
+    """LIST mode over gloo: the per-shard truncated above-GT lists travel in one all-gather, and the exact recount of
+    the pairs rank 0 could not settle is served by every rank over its own columns (sharded.unlisted_round)."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import mmx
+    from mmx.ops import ProtocolRanks
+    rs = np.random.RandomState(1)
+    nq, n_cols, cap, B = 40, 333, 6, 9
+    scores = torch.from_numpy(rs.randn(nq, n_cols).astype(np.float32))
+    gt_sets = [[int(rs.randint(n_cols))] for _ in range(nq)]
+    mult = torch.from_numpy(rs.poisson(1.0, size=(B, n_cols)).astype(np.uint8))
+    bounds = mmx.sharded.shard_bounds(n_cols, world)
+    a, b = bounds[rank]
+    thr = mmx.sharded.merge_thresholds(_local_structures(scores, gt_sets, a, b))
+    above = scores[:, a:b] > thr[:, None]
+    list_i = torch.full((1, nq, cap), -7, dtype=torch.int32)
+    list_n = torch.zeros((1, nq), dtype=torch.int32)
+    for q in range(nq):
+        cols = (torch.nonzero(above[q]).flatten() + a).to(torch.int32)
+        list_n[0, q] = len(cols) + (1 if len(cols) > cap else 0)          # the cursor may overshoot the capacity
+        list_i[0, q, : min(len(cols), cap)] = cols[:cap]
+    local = ProtocolRanks(thr=thr, cnt_above=above.sum(1).to(torch.int32), bits=None, n_cols=b - a, list_i=list_i,
+                          list_n=list_n)
+    merged = mmx.sharded.merge_ranks(local, bounds)
+    full_above = scores > thr[:, None]
+    ok = torch.equal(merged.cnt_above, full_above.sum(1).to(torch.int32)) and merged.list_i.shape == (world, nq, cap)
+    for q in range(nq):
+        got = [int(c) for r in range(world) for c in merged.list_i[r, q, : min(int(merged.list_n[r, q]), cap)]]
+        ok = ok and all(bool(full_above[q, c]) for c in got) and len(set(got)) == len(got)
+        if int(merged.cnt_above[q]) <= cap:
+            ok = ok and sorted(got) == torch.nonzero(full_above[q]).flatten().tolist()
+
+    def local_resolve(pairs, mult_rows):        # this shard's share: sum_{col in [a, b)} m[b, col] * above[q, col]
+        return (mult_rows[pairs[:, 0].long()][:, a:b].long() * above[pairs[:, 1].long()].long()).sum(1)
+    if rank == 0:
+        pairs = torch.tensor([[0, 3], [2, 17], [1, 3], [2, 39]], dtype=torch.int32)
+        rows = mult[[4, 0, 8]].contiguous()                              # pairs[:, 0] indexes these rows
+        c = mmx.sharded.unlisted_round(local_resolve, pairs, rows)
+        want = (rows[pairs[:, 0].long()].long() * full_above[pairs[:, 1].long()].long()).sum(1)
+        ok = ok and torch.equal(c, want)
+        ok = ok and mmx.sharded.unlisted_round(local_resolve, None, None) is None      # a K3 call with nothing unsettled
+    else:
+        ok = ok and mmx.sharded.unlisted_round(local_resolve, None, None) is not None
+        ok = ok and mmx.sharded.unlisted_round(local_resolve, None, None) is None
+    Path(out_dir, f"ok{rank}").write_text("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_list_mode_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_worker_lists, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert [Path(tmp_path, f"ok{r}").read_text() for r in range(world)] == ["1", "1"]
+
+
 def test_shard_bounds():
     sys.path.insert(0, str(ROOT))
     import mmx
