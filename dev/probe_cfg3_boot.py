@@ -57,13 +57,20 @@ def step():
 for it in range(2):
     out = step(); torch.cuda.synchronize()
     if world > 1: dist.barrier()
+# the plain COUNT pass (no lists, no bitmask) on the same operands, for comparison
+thr_all = sharded.merge_thresholds(ops.dense_rank(txt, G, off, idx, want_bits=False, g_base=a, threshold_only=True).thr)
+pe = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+ops.dense_rank(txt, G, off, idx, want_bits=False, g_base=a, thr=thr_all)
+pe[0].record(); plain = ops.dense_rank(txt, G, off, idx, want_bits=False, g_base=a, thr=thr_all); pe[1].record()
+torch.cuda.synchronize()
 if rank == 0:
     ranks, vals, st = out
     ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(5)]
     cnt = ranks.cnt_above
     print(json.dumps({"workload": f"dense {N} x {N} x {D} T2I + {B}-iteration bootstrap, LIST mode (cap {ops.LIST_CAP})",
                       "n_gpus": world, "ms": {"threshold_pass": ms[0], "count_and_list_pass": ms[1], "numpy_stream_on_device": ms[2],
-                                              "bincount": ms[3], "K3_lists": ms[4], "total": sum(ms)},
+                                              "bincount": ms[3], "K3_lists": ms[4], "total": sum(ms),
+                                              "plain_count_pass_for_comparison": pe[0].elapsed_time(pe[1])},
                       "base_R@1/5/10": [100.0 * int((cnt < k).sum()) / N for k in (1, 5, 10)],
                       "boot_mean_R@1/5/10": vals.mean(0).tolist(), "boot_std": vals.std(0).tolist(),
                       "queries_with_truncated_list": int((cnt > ops.LIST_CAP).sum()), "unresolved_pairs": st.get("unresolved_pairs")}), flush=True)

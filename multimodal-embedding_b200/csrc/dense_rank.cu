@@ -24,12 +24,22 @@
 #include <cfloat>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "../../include/mmx.h"
 #include "mmx_host.cuh"
 #include "sm100_ptx.cuh"
 #include "topk.cuh"
 
 #define MMX_MODE_GROUPMAX 2   // internal to mmx_dense_topk
+#define MMX_MODE_LISTS 3      // internal to mmx_dense_rank_lists: count + above-GT column lists, no bitmask
+// Optional outputs of the COUNT pass, compile-time (FEAT template parameter): with all of them behind run-time flags
+// the unrolled epilogue was ~200 KB of SASS and the pass lost 7 % (5000 x 25 000) to 27 % (10^6 x 10^6) of its
+// throughput to instruction-cache misses; every caller wants at most one of them.
+#define MMX_FEAT_NONE 0    // counts (+ bitmask): the ranking pass of every dense model
+#define MMX_FEAT_GRP 1     // + group maxima for the top-k bound (mmx_dense_rank_topk)
+#define MMX_FEAT_CAND 2    // + (score, column) candidates above the bar (second pass of the matrix-free top-k)
+#define MMX_FEAT_SCORES 3  // + the fp32 scores themselves (compute_similarity_scores drop-in, small-gallery top-k)
 
 namespace mmx {
 namespace dense {
@@ -92,9 +102,28 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
         atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// MODE_LISTS: write the columns of the recorded hit words into the list slots [base, base + hits) that were reserved
+// for them (slots beyond the capacity are dropped) and clear the words.
+__device__ __forceinline__ void flush_pending(const Params& p, uint32_t (&bits)[BN / 32], int base, long long q,
+                                              long long n0) {
+    int slot = base;
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) {
+        uint32_t w = bits[c];
+        bits[c] = 0u;
+        while (w != 0u && slot < p.cand_cap) {
+            const int j = __ffs(w) - 1;
+            w &= w - 1u;
+            p.cand_i[q * p.cand_cap + slot] = (int32_t)(p.g_base + n0 + c * 32 + j);
+            ++slot;
+        }
+        slot += __popc(w);  // hits that found the list full still own their slots
+    }
+}
+
 // MODE is a template parameter: each pass gets an epilogue without the other passes' code (the threshold pass
 // indexes the accumulator registers dynamically, which would put the COUNT pass's registers on the stack too).
-template <int MODE>
+template <int MODE, int FEAT = MMX_FEAT_NONE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                   const __grid_constant__ Params p) {
@@ -176,6 +205,11 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const uint32_t acc = (warp - 4) >> 2;  // which 128-row half of every tile this warp drains
         const int row = acc * BM + wq * 32 + lane;
         uint32_t tc = 0;
+        // MODE_LISTS: hit words of the last drained tile, their row / first column and the reserved list slots
+        uint32_t pend_bits[BN / 32];
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) pend_bits[c] = 0u;
+        int pend_base = 0, pend_m = 0, pend_nt = 0;  // reserved slots, row tile and column tile of those hits
         for (int i = blockIdx.x; i < n_work; i += gridDim.x, ++tc) {
             int m_blk, n_tile;
             tile_coords(p, tile_id(p, i), m_blk, n_tile);
@@ -193,7 +227,13 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             bool emit = false;
             if (MODE == MMX_MODE_COUNT) {
                 if (valid_row) thr = __ldg(p.thr + q);
-                emit = p.cand_n != nullptr && valid_row && __ldcg(p.cand_n + q) <= p.cand_cap;
+                if (FEAT == MMX_FEAT_CAND) emit = valid_row && __ldcg(p.cand_n + q) <= p.cand_cap;
+            } else if (MODE == MMX_MODE_LISTS) {
+                if (valid_row) thr = __ldg(p.thr + q);
+                emit = valid_row && __ldcg(p.cand_n + q) <= p.cand_cap;
+                // the hits of the PREVIOUS tile go to the slots reserved at its end: that atomic has long returned, and
+                // the tensor core is still busy with this tile, so the list stores cost the pipeline nothing
+                flush_pending(p, pend_bits, pend_base, (long long)pend_m * TM + row, (long long)pend_nt * BN);
             } else if (MODE == MMX_MODE_THRESHOLD && valid_row) {
                 e0 = __ldg(p.gt_off + q);
                 e1 = __ldg(p.gt_off + q + 1);
@@ -204,12 +244,18 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             float best = -INFINITY;
             uint32_t vbuf[2][32];
             tmem_ld_32x32(taddr, vbuf[0]);
+            // eight 32-column chunks as four pairs (the two register buffers alternate inside a pair). The candidate
+            // variant keeps the pair loop rolled: its per-column append code is 8x smaller that way (117 -> ~30 KB)
+            constexpr int PAIR_UNROLL = (MODE == MMX_MODE_COUNT && FEAT == MMX_FEAT_CAND) ? 1 : BN / 64;
+#pragma unroll PAIR_UNROLL
+            for (int cp = 0; cp < BN / 64; ++cp)
 #pragma unroll
-            for (int ch = 0; ch < BN / 32; ++ch) {
-                uint32_t (&v)[32] = vbuf[ch & 1];
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int ch = cp * 2 + h2;
+                uint32_t (&v)[32] = vbuf[h2];
                 tmem_ld_wait();
                 if (ch + 1 < BN / 32) {
-                    tmem_ld_32x32(taddr + (ch + 1) * 32, vbuf[(ch + 1) & 1]);  // in flight while this chunk is ranked
+                    tmem_ld_32x32(taddr + (ch + 1) * 32, vbuf[h2 ^ 1]);  // in flight while this chunk is ranked
                 } else {
                     // the whole accumulator half is in registers: hand it back to the MMA warp
                     tc_fence_before();
@@ -226,6 +272,15 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                         best = fmaxf(best, m);
                     else if (valid_row && nvalid > 0)
                         p.grp_max[q * p.n_grp + (c0 >> 5)] = m;
+                } else if (MODE == MMX_MODE_LISTS) {
+                    const long long nvalid = p.ng - c0;
+                    const uint32_t cmask = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << (int)nvalid) - 1u));
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
+                    bits &= cmask;
+                    cnt += __popc(bits);
+                    pend_bits[ch] = emit ? bits : 0u;
                 } else if (MODE == MMX_MODE_COUNT) {
                     const long long nvalid = p.ng - c0;
                     const uint32_t cmask = nvalid >= 32 ? 0xffffffffu : (nvalid <= 0 ? 0u : ((1u << (int)nvalid) - 1u));
@@ -234,7 +289,7 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     for (int j = 0; j < 32; ++j) bits |= (__uint_as_float(v[j]) > thr ? 1u : 0u) << j;
                     bits &= cmask;
                     cnt += __popc(bits);
-                    if (p.grp_max != nullptr) {  // fused group maxima for the top-k bound (mmx_dense_rank_topk)
+                    if (FEAT == MMX_FEAT_GRP) {  // fused group maxima for the top-k bound (mmx_dense_rank_topk)
                         float m = -INFINITY;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) m = fmaxf(m, j < nvalid ? __uint_as_float(v[j]) : -INFINITY);
@@ -246,19 +301,19 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     const long long w = (c0 >> 5);
                     if (p.above_bits != nullptr && valid_row && w < p.words_per_row)
                         p.above_bits[q * p.words_per_row + w] = bits;
-                    if (emit && bits != 0u) {   // a handful of hits per row (top-k bar), or a row whose list is not full yet
+                    if (FEAT == MMX_FEAT_CAND && emit && bits != 0u) {   // a handful of hits per row (bar just below the k-th group maximum)
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             if ((bits >> j) & 1u) {
                                 const int slot = atomicAdd(p.cand_n + q, 1);
                                 if (slot < p.cand_cap) {
-                                    if (p.cand_s != nullptr) p.cand_s[q * p.cand_cap + slot] = __uint_as_float(v[j]);
+                                    p.cand_s[q * p.cand_cap + slot] = __uint_as_float(v[j]);
                                     p.cand_i[q * p.cand_cap + slot] = (int32_t)(p.g_base + c0 + j);
                                 }
                             }
                         }
                     }
-                    if (p.scores != nullptr && valid_row) {
+                    if (FEAT == MMX_FEAT_SCORES && valid_row) {
                         float* dst = p.scores + q * p.ld_scores + c0;
                         if (nvalid >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
@@ -283,15 +338,26 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     }
                 }
             }
-            if (MODE == MMX_MODE_COUNT) {
+            if (MODE == MMX_MODE_LISTS) {
                 if (valid_row && cnt > 0) atomicAdd(p.cnt_above + q, cnt);
-                if (p.grp_max != nullptr && p.grp_tile && valid_row) p.grp_max[q * p.n_grp + n_tile] = best;
+                // reserve list slots for this tile's hits; the result is only used at the start of the next tile
+                int tot = 0;
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) tot += __popc(pend_bits[c]);
+                if (tot > 0) pend_base = atomicAdd(p.cand_n + q, tot);
+                pend_m = m_blk;
+                pend_nt = n_tile;
+            } else if (MODE == MMX_MODE_COUNT) {
+                if (valid_row && cnt > 0) atomicAdd(p.cnt_above + q, cnt);
+                if (FEAT == MMX_FEAT_GRP && p.grp_tile && valid_row) p.grp_max[q * p.n_grp + n_tile] = best;
             } else if (MODE == MMX_MODE_GROUPMAX) {
                 if (p.grp_tile && valid_row) p.grp_max[q * p.n_grp + n_tile] = best;
             } else if (valid_row && best > -INFINITY) {
                 atomic_max_float(p.thr + q, best);
             }
         }
+        if (MODE == MMX_MODE_LISTS)
+            flush_pending(p, pend_bits, pend_base, (long long)pend_m * TM + row, (long long)pend_nt * BN);
     }
 
     tc_fence_before();
@@ -330,31 +396,38 @@ extern "C" int mmx_dense_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes) 
     return 0;
 }
 
+template <int MODE, int FEAT>
+static int launch_variant(const CUtensorMap& tq, const CUtensorMap& tg, const Params& p, cudaStream_t stream) {
+    const size_t smem_bytes = sizeof(Smem) + 1024;
+    static const char attr_set_tag = 0;  // one per template instantiation
+    if (first_use_on_device(&attr_set_tag))
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MODE, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem_bytes));
+    const int sms = sm_count();
+    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
+    dense_rank_kernel<MODE, FEAT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 static int launch_dense(const void* Q, int64_t nq, const void* G, int64_t ng, int d, const Params& p,
                         cudaStream_t stream) {
     CUtensorMap tq, tg;
     if (make_tmap_bf16_sw128(&tq, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, BM) != 0) return -4;
     if (make_tmap_bf16_sw128(&tg, G, (uint64_t)ng, (uint64_t)d, (uint64_t)d, BN) != 0) return -4;
-    const size_t smem_bytes = sizeof(Smem) + 1024;
-    static const char attr_set_tag = 0;
-    if (first_use_on_device(&attr_set_tag)) {
-        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_THRESHOLD>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_COUNT>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MMX_MODE_GROUPMAX>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    if (p.mode == MMX_MODE_THRESHOLD) return launch_variant<MMX_MODE_THRESHOLD, MMX_FEAT_NONE>(tq, tg, p, stream);
+    if (p.mode == MMX_MODE_GROUPMAX) return launch_variant<MMX_MODE_GROUPMAX, MMX_FEAT_NONE>(tq, tg, p, stream);
+    if (p.mode == MMX_MODE_LISTS) return launch_variant<MMX_MODE_LISTS, MMX_FEAT_NONE>(tq, tg, p, stream);
+    // MMX_MODE_COUNT: at most one optional output per pass
+    const int n_opt = (p.grp_max != nullptr) + (p.cand_n != nullptr) + (p.scores != nullptr);
+    MMX_REQUIRE(n_opt <= 1, "COUNT pass: group maxima, candidates and scores are mutually exclusive");
+    if (p.grp_max != nullptr) return launch_variant<MMX_MODE_COUNT, MMX_FEAT_GRP>(tq, tg, p, stream);
+    if (p.cand_n != nullptr) {
+        MMX_REQUIRE(p.cand_s != nullptr && p.cand_i != nullptr, "candidate buffers missing");
+        return launch_variant<MMX_MODE_COUNT, MMX_FEAT_CAND>(tq, tg, p, stream);
     }
-    const int sms = sm_count();
-    const int grid = p.n_tiles < sms ? p.n_tiles : sms;
-    if (p.mode == MMX_MODE_COUNT)
-        dense_rank_kernel<MMX_MODE_COUNT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
-    else if (p.mode == MMX_MODE_THRESHOLD)
-        dense_rank_kernel<MMX_MODE_THRESHOLD><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
-    else
-        dense_rank_kernel<MMX_MODE_GROUPMAX><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
-    MMX_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    if (p.scores != nullptr) return launch_variant<MMX_MODE_COUNT, MMX_FEAT_SCORES>(tq, tg, p, stream);
+    return launch_variant<MMX_MODE_COUNT, MMX_FEAT_NONE>(tq, tg, p, stream);
 }
 
 static int base_params(Params& p, int64_t nq, int64_t ng, int d) {
@@ -667,6 +740,6 @@ extern "C" int mmx_dense_rank_lists(const void* Q, int64_t nq, const void* G, in
     p.cand_i = list_i;
     p.cand_n = list_n;
     p.cand_cap = cap;
-    p.mode = MMX_MODE_COUNT;
+    p.mode = MMX_MODE_LISTS;
     return launch_dense(Q, nq, G, ng, d, p, stream);
 }
