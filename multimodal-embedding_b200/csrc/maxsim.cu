@@ -38,7 +38,9 @@
 // reference's zero padding). Boundaries then fall on 4-column groups and are the same for every thread, so the drain
 // is branch-uniform: 8 group maxima per 32-column chunk, a running maximum, and one shared-memory store per closed
 // document into M[accumulator][slot][row] (at most 16 documents end inside one 256-column tile). Warps 4-7 drain
-// accumulator 0 and warps 8-11 accumulator 1 (all 256 columns each: no half merging), and two reducer warps (2 and 3,
+// accumulator 0 and warps 8-11 accumulator 1; every thread walks the columns [0,128) and [128,256) of its row as two
+// interleaved chains (instruction-level parallelism for the latency-bound running maximum) and joins them at the end
+// of the tile. Two reducer warps (2 and 3,
 // one per accumulator) sum the rows of a whole tile's documents at once, two lanes per document, instead of one
 // latency-bound shuffle tree per document.
 #include <cfloat>
@@ -69,6 +71,7 @@ constexpr int SHORT_ALIGN = 4;                   // SHORT variant: padded docume
 constexpr int SHORT_MIN = 16;                    // ... and at least this, so at most BN / SHORT_MIN documents end per tile
 constexpr int MSLOTS = BN / SHORT_MIN;           // 16
 constexpr int MSTRIDE = BM + 1;                  // row pitch of M in floats: slot * 129 + row is conflict-free both ways
+constexpr uint32_t MBUF_BYTES = 2 * MSLOTS * MSTRIDE * 4;  // one M buffer (both accumulators)
 constexpr long long SHORT_AVG_ROWS = 256;        // documents shorter than this on average take the SHORT variant
 
 struct Params {
@@ -89,17 +92,22 @@ struct __align__(1024) Smem {
     uint8_t b[NSTAGE][B_STAGE_BYTES];
     union {
         float stage[2][NSLOT][2][BM];  // [accumulator][slot][column half][row] row maxima of a closed document
-        float M[2][MSLOTS][MSTRIDE];   // SHORT: [accumulator][document slot][row] row maxima of a tile's documents
+        // SHORT: [buffer][accumulator][document slot][row] row maxima of a tile's documents. Two buffers per
+        // accumulator: the reducer sums tile t while the drain warps already fill tile t + 1 (with one buffer the two
+        // were serialised, T_reduce + T_drain = 2900 clk per 2048 clk of MMA: tensor pipe 70 %)
+        float M[2][2][MSLOTS][MSTRIDE];
     };
-    int seg_start[2][BM + 1];      // reducer-private: query segments of the two row tiles
+    uint8_t seg_start[2][BM + 4];  // reducer-private: query segments of the two row tiles (row boundaries 0..128)
     int seg_q[2][BM];
     uint64_t a_full, a_free;
     uint64_t b_full[NSTAGE], b_empty[NSTAGE];
     uint64_t t_full[2], t_empty[2];
     uint64_t st_full[2][NSLOT], st_empty[2][NSLOT];
-    uint64_t batch_full[2], batch_empty[2];  // SHORT: M[a] written by the 4 drain warps / consumed by the reducer
+    uint64_t batch_full[2][2], batch_empty[2][2];  // SHORT, [accumulator][buffer]: M written by the 4 drain warps / consumed by the reducer
     uint32_t tmem_base;
 };
+
+static_assert(sizeof(Smem) + 1024 <= 227 * 1024, "Smem (+ alignment slack) exceeds the 227 KB a CTA can opt into");
 
 struct ItemGeom {
     int mp, d0, d1, p0, p1, ntiles;
@@ -286,7 +294,7 @@ __device__ __forceinline__ int build_segments(Smem& s, const Params& p, int tb, 
         const uint32_t hmask = __ballot_sync(0xffffffffu, head);
         if (head) {
             const int idx = nseg + __popc(hmask & ((1u << lane) - 1u));
-            s.seg_start[tb][idx] = row;
+            s.seg_start[tb][idx] = (uint8_t)row;
             s.seg_q[tb][idx] = q;
         }
         nseg += __popc(hmask);
@@ -360,27 +368,39 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 
-// 32 accumulator columns = 8 groups of 4; e8 = which groups end a document (same for every thread of the CTA).
-// addr = shared-space byte address of M[accumulator][next free slot][row]; a closed document's maximum is stored
-// there and the address moves on one slot. Branch-free: one predicate per group drives the store, the reset of the
-// running maximum and the address step.
-__device__ __forceinline__ void fold_short(const uint32_t (&v)[32], float& m, uint32_t e8, uint32_t& addr) {
-    float g4[8];
+// 16 columns = 4 groups of 4 of EACH of two independent column chains (A: the tile's columns [0,128), B: [128,256));
+// eA / eB = which of those groups end a document (the same for every thread of the CTA). addr = shared-space byte
+// address of M[accumulator][next free slot][row] of the chain; a closed document's maximum is stored there and the
+// address moves on one slot. Branch-free: one predicate per group drives the store, the reset of the running maximum
+// and the address step. The chains are interleaved group by group: every chain is a serial FMNMX -> select -> FMNMX
+// dependency through its running maximum, and one chain alone left the drain warp waiting on ALU latency for a third of its cycles (ncu: stall_wait 30 %,
+// IPC 0.34 while draining). Two chains give the scheduler an independent instruction for every dependent one.
+__device__ __forceinline__ void fold_short2(const uint32_t (&a)[16], const uint32_t (&b)[16], float& mA, float& mB,
+                                            uint32_t eA, uint32_t eB, uint32_t& addrA, uint32_t& addrB) {
+    float gA[4], gB[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        g4[k] = fmaxf(max3(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2])),
-                      __uint_as_float(v[4 * k + 3]));
+    for (int k = 0; k < 4; ++k) {
+        gA[k] = fmaxf(max3(__uint_as_float(a[4 * k]), __uint_as_float(a[4 * k + 1]), __uint_as_float(a[4 * k + 2])),
+                      __uint_as_float(a[4 * k + 3]));
+        gB[k] = fmaxf(max3(__uint_as_float(b[4 * k]), __uint_as_float(b[4 * k + 1]), __uint_as_float(b[4 * k + 2])),
+                      __uint_as_float(b[4 * k + 3]));
+    }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        m = fmaxf(m, g4[k]);
+    for (int k = 0; k < 4; ++k) {
+        mA = fmaxf(mA, gA[k]);
+        mB = fmaxf(mB, gB[k]);
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "setp.ne.b32 p, %2, 0;\n\t"
+            "{\n\t.reg .pred p, q;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "setp.ne.b32 q, %5, 0;\n\t"
             "@p st.shared.f32 [%0], %1;\n\t"
+            "@q st.shared.f32 [%2], %3;\n\t"
             "@p mov.b32 %1, 0xff800000;\n\t"
-            "@p add.u32 %0, %0, %3;\n\t}"
-            : "+r"(addr), "+f"(m)
-            : "r"(e8 & (1u << k)), "n"(MSTRIDE * 4)
+            "@q mov.b32 %3, 0xff800000;\n\t"
+            "@p add.u32 %0, %0, %6;\n\t"
+            "@q add.u32 %2, %2, %6;\n\t}"
+            : "+r"(addrA), "+f"(mA), "+r"(addrB), "+f"(mB)
+            : "r"(eA & (1u << k)), "r"(eB & (1u << k)), "n"(MSTRIDE * 4)
             : "memory");
     }
 }
@@ -412,7 +432,7 @@ __device__ __forceinline__ void short_reducer(Smem& s, const Params& p, int a, i
         int first = g.d0;
         uint64_t ends_next = tile_ends(p, g.p0, g.p1);
         uint8_t zflag_next = (flags && first + j < p.nd) ? __ldg(p.d_zero + first + j) : (uint8_t)0;
-        const uint32_t M = smem_u32(&s.M[a][j][0]);
+        const uint32_t M0 = smem_u32(&s.M[0][a][j][0]);
         for (int t = 0; t < g.ntiles; ++t, ++use) {
             const uint64_t ends = ends_next;
             const uint8_t zflag = zflag_next;
@@ -425,7 +445,8 @@ __device__ __forceinline__ void short_reducer(Smem& s, const Params& p, int a, i
             const bool act = j < n;
             const int doc = first + j;
             const float floor_v = (act && zflag) ? 0.0f : -INFINITY;  // max(x, -inf) = x: one code path for both
-            mbar_wait(&s.batch_full[a], use & 1);
+            const uint32_t M = M0 + (use & 1u) * MBUF_BYTES;
+            mbar_wait(&s.batch_full[a][use & 1], (use >> 1) & 1);
 #pragma unroll 1
             for (int si = 0; si < nseg; ++si) {
                 const int ra = s.seg_start[a][si], rb = s.seg_start[a][si + 1];
@@ -471,7 +492,7 @@ __device__ __forceinline__ void short_reducer(Smem& s, const Params& p, int a, i
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s.batch_empty[a]);
+            if (lane == 0) mbar_arrive(&s.batch_empty[a][use & 1]);
             first += n;
         }
     }
@@ -500,8 +521,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.t_full[i], 1);
             mbar_init(&s.t_empty[i], SHORT ? 4 : 8);  // one arrival per drain warp of this accumulator
-            mbar_init(&s.batch_full[i], 4);
-            mbar_init(&s.batch_empty[i], 1);
+            for (int j = 0; j < 2; ++j) {
+                mbar_init(&s.batch_full[i][j], 4);
+                mbar_init(&s.batch_empty[i][j], 1);
+            }
             for (int j = 0; j < NSLOT; ++j) {
                 mbar_init(&s.st_full[i][j], 8);
                 mbar_init(&s.st_empty[i][j], 1);
@@ -618,7 +641,7 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         const int a = (warp - 4) >> 2;
         const int row = (warp & 3) * 32 + lane;
         const uint32_t ta = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + a * BN;
-        const uint32_t Mrow = smem_u32(&s.M[a][0][0]) + 4u * (uint32_t)row;
+        const uint32_t Mrow0 = smem_u32(&s.M[0][a][0][0]) + 4u * (uint32_t)row;
         uint32_t use = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const ItemGeom g = item_geom(p, item);
@@ -634,36 +657,43 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 const uint32_t elo = (uint32_t)ends, ehi = (uint32_t)(ends >> 32);
                 mbar_wait(&s.t_full[a], use & 1);
                 tc_fence_after();
-                uint32_t va[32], vb[32];
-                tmem_ld_32x32(ta, va);
-                mbar_wait(&s.batch_empty[a], (use & 1) ^ 1);  // the reducer is done with this accumulator's last tile
-                uint32_t addr = Mrow;
-                tmem_ld_wait();
-                tmem_ld_32x32(ta + 32, vb);
-                fold_short(va, m, elo & 0xffu, addr);
-                tmem_ld_wait();
-                tmem_ld_32x32(ta + 64, va);
-                fold_short(vb, m, (elo >> 8) & 0xffu, addr);
-                tmem_ld_wait();
-                tmem_ld_32x32(ta + 96, vb);
-                fold_short(va, m, (elo >> 16) & 0xffu, addr);
-                tmem_ld_wait();
-                tmem_ld_32x32(ta + 128, va);
-                fold_short(vb, m, elo >> 24, addr);
-                tmem_ld_wait();
-                tmem_ld_32x32(ta + 160, vb);
-                fold_short(va, m, ehi & 0xffu, addr);
-                tmem_ld_wait();
-                tmem_ld_32x32(ta + 192, va);
-                fold_short(vb, m, (ehi >> 8) & 0xffu, addr);
-                tmem_ld_wait();
-                tmem_ld_32x32(ta + 224, vb);
-                fold_short(va, m, (ehi >> 16) & 0xffu, addr);
-                tmem_ld_wait();
-                release_accumulator(s, a, lane);
-                fold_short(vb, m, ehi >> 24, addr);
+                // two column chains per thread: A walks the tile's columns [0,128), B [128,256), 16 columns of each
+                // per step; B's documents take the slots after A's (their number is known from the boundary word)
+                uint32_t a0[16], b0[16], a1[16], b1[16];
+                tmem_ld_32x16(ta, a0);
+                tmem_ld_32x16(ta + 128, b0);
+                // the reducer is done with the tile that used this buffer two tiles ago
+                mbar_wait(&s.batch_empty[a][use & 1], ((use >> 1) & 1) ^ 1);
+                const uint32_t Mrow = Mrow0 + (use & 1u) * MBUF_BYTES;
+                uint32_t addrA = Mrow;
+                const uint32_t addrB0 = Mrow + (uint32_t)__popc(elo) * (MSTRIDE * 4);
+                uint32_t addrB = addrB0;
+                float mB = -INFINITY;
+#pragma unroll
+                for (int st = 0; st < 8; st += 2) {
+                    tmem_ld_wait();
+                    tmem_ld_32x16(ta + 16 * (st + 1), a1);
+                    tmem_ld_32x16(ta + 128 + 16 * (st + 1), b1);
+                    fold_short2(a0, b0, m, mB, (elo >> (4 * st)) & 0xfu, (ehi >> (4 * st)) & 0xfu, addrA, addrB);
+                    tmem_ld_wait();
+                    if (st + 2 < 8) {
+                        tmem_ld_32x16(ta + 16 * (st + 2), a0);
+                        tmem_ld_32x16(ta + 128 + 16 * (st + 2), b0);
+                    } else {
+                        release_accumulator(s, a, lane);
+                    }
+                    fold_short2(a1, b1, m, mB, (elo >> (4 * st + 4)) & 0xfu, (ehi >> (4 * st + 4)) & 0xfu, addrA, addrB);
+                }
+                // join the chains: the document that was open at column 128 belongs to B's first closed document, or,
+                // if B closed none, to the maximum carried into the next tile
+                if (ehi != 0u) {
+                    sts_f32(addrB0, fmaxf(lds_f32(addrB0), m));
+                    m = mB;
+                } else {
+                    m = fmaxf(m, mB);
+                }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s.batch_full[a]);
+                if (lane == 0) mbar_arrive(&s.batch_full[a][use & 1]);
             }
         }
     } else if (warp >= 4) {
