@@ -659,9 +659,15 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 tc_fence_after();
                 // two column chains per thread: A walks the tile's columns [0,128), B [128,256), 16 columns of each
                 // per step; B's documents take the slots after A's (their number is known from the boundary word)
-                uint32_t a0[16], b0[16], a1[16], b1[16];
-                tmem_ld_32x16(ta, a0);
-                tmem_ld_32x16(ta + 128, b0);
+                // NBUF register buffers per chain: the loads run NBUF - 1 steps ahead of the folds, so the accumulator
+                // goes back to the tensor core after 9 - NBUF of the eight folds
+                constexpr int NBUF = 4;
+                uint32_t va[NBUF][16], vb[NBUF][16];
+#pragma unroll
+                for (int i = 0; i < NBUF - 1; ++i) {
+                    tmem_ld_32x16(ta + 16 * i, va[i]);
+                    tmem_ld_32x16(ta + 128 + 16 * i, vb[i]);
+                }
                 // the reducer is done with the tile that used this buffer two tiles ago
                 mbar_wait(&s.batch_empty[a][use & 1], ((use >> 1) & 1) ^ 1);
                 const uint32_t Mrow = Mrow0 + (use & 1u) * MBUF_BYTES;
@@ -670,19 +676,17 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 uint32_t addrB = addrB0;
                 float mB = -INFINITY;
 #pragma unroll
-                for (int st = 0; st < 8; st += 2) {
-                    tmem_ld_wait();
-                    tmem_ld_32x16(ta + 16 * (st + 1), a1);
-                    tmem_ld_32x16(ta + 128 + 16 * (st + 1), b1);
-                    fold_short2(a0, b0, m, mB, (elo >> (4 * st)) & 0xfu, (ehi >> (4 * st)) & 0xfu, addrA, addrB);
-                    tmem_ld_wait();
-                    if (st + 2 < 8) {
-                        tmem_ld_32x16(ta + 16 * (st + 2), a0);
-                        tmem_ld_32x16(ta + 128 + 16 * (st + 2), b0);
-                    } else {
-                        release_accumulator(s, a, lane);
+                for (int st = 0; st < 8; ++st) {
+                    // everything issued so far has landed (the later steps were issued at least a whole fold ago)
+                    if (st + NBUF - 1 <= 8) tmem_ld_wait();
+                    if (st + NBUF - 1 < 8) {
+                        tmem_ld_32x16(ta + 16 * (st + NBUF - 1), va[(st + NBUF - 1) % NBUF]);
+                        tmem_ld_32x16(ta + 128 + 16 * (st + NBUF - 1), vb[(st + NBUF - 1) % NBUF]);
+                    } else if (st + NBUF - 1 == 8) {
+                        release_accumulator(s, a, lane);  // all 256 columns of this row are in registers
                     }
-                    fold_short2(a1, b1, m, mB, (elo >> (4 * st + 4)) & 0xfu, (ehi >> (4 * st + 4)) & 0xfu, addrA, addrB);
+                    fold_short2(va[st % NBUF], vb[st % NBUF], m, mB, (elo >> (4 * st)) & 0xfu, (ehi >> (4 * st)) & 0xfu,
+                                addrA, addrB);
                 }
                 // join the chains: the document that was open at column 128 belongs to B's first closed document, or,
                 // if B closed none, to the maximum carried into the next tile
