@@ -49,6 +49,13 @@ def test_empty_inputs(mmx_mod):
     assert torch.all(ti == -1) and torch.all(torch.isinf(ts))
     ts, ti = ops.topk_from_scores(torch.empty(3, 0, dtype=torch.float32, device=dev), 10)
     assert tuple(ti.shape) == (3, 10) and torch.all(ti == -1)
+    # LIST mode on an empty gallery: nothing is above anything, every drawn query copy is a hit (min(m_q, k) of them)
+    rl = ops.dense_rank_lists(Q, torch.empty(0, 64, dtype=torch.bfloat16, device=dev), gt_off,
+                              torch.zeros(5, dtype=torch.int32, device=dev))
+    assert torch.all(rl.cnt_above == 0) and torch.all(rl.list_n == 0)
+    mult = torch.tensor([[2, 0, 1, 1, 0], [0, 0, 0, 3, 1]], dtype=torch.uint8, device=dev)
+    correct = ops.boot_counts_lists(rl, mult, resolve=None)
+    assert correct.cpu().tolist() == [[3, 4, 4], [2, 4, 4]]
 
 
 @pytest.mark.parametrize("nq,ng,d", [(1, 1, 8), (1, 300, 16), (255, 257, 64), (256, 256, 72), (257, 255, 1152), (513, 1, 128)])
@@ -67,6 +74,14 @@ def test_dense_sizes_around_tile_boundaries(mmx_mod, nq, ng, d):
     ts, ti = mmx_mod.ops.dense_topk(Q.to(dev), G.to(dev), 10)
     wv, wi = oracle.topk_lists(S, 10)
     assert torch.equal(ts.cpu(), wv) and torch.equal(ti.cpu().long(), wi)
+    # LIST mode around the same tile boundaries: exact counts, and the lists hold min(count, cap) distinct set columns
+    rl = mmx_mod.ops.dense_rank_lists(Q.to(dev), G.to(dev), torch.from_numpy(off).to(dev), torch.from_numpy(idx).to(dev), cap=8)
+    assert torch.equal(rl.cnt_above, r.cnt_above)
+    above = (S > thr[:, None]).numpy()
+    li, ln = rl.list_i[0].cpu().numpy(), rl.list_n[0].cpu().numpy()
+    for q in range(nq):
+        n = min(int(ln[q]), 8)
+        assert n == min(int(above[q].sum()), 8) and above[q, li[q, :n]].all() and len(set(li[q, :n].tolist())) == n
 
 
 def test_argument_errors_are_exceptions(mmx_mod):
