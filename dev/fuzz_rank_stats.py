@@ -69,6 +69,22 @@ for case in range(n_cases):
     mq = m[:, r.q_unit.cpu().numpy()]
     want = np.stack([np.minimum(mq, np.maximum(0, kk_ - c)).sum(1) for kk_ in (1, 5, 10)], axis=1)
     assert np.array_equal(got, want), ("K3", case)
+    # ---------------- LIST mode: exact counts, lists inside the above-GT set, K3 on lists == the identity above
+    cap = int(rs.choice([1, 3, 8, 64]))
+    has_gt_d = torch.from_numpy(np.array([len(x) > 0 for x in gt])).to(dev)
+    rl = ops.dense_rank_lists(Q, G, off_d, idx_d, g_base=g_base, thr=r.thr, cap=cap)
+    assert torch.equal(rl.cnt_above, r.cnt_above), ("lists cnt", case)
+    li, ln = rl.list_i[0].cpu().numpy() - g_base, rl.list_n[0].cpu().numpy()
+    ab = above.numpy()
+    for q in range(nq):
+        nv = min(int(ln[q]), cap)
+        assert nv == min(int(ab[q].sum()), cap) and ab[q, li[q, :nv]].all() and len(set(li[q, :nv].tolist())) == nv, ("lists", case, q)
+    full_map = torch.zeros(g_base + ng, dtype=torch.int32, device=dev)
+    full_map[g_base:] = r.col2unit                                                  # lists carry GLOBAL column ids
+    rl.col2unit, rl.q_unit = full_map, r.q_unit
+    st = {}
+    got_l = ops.boot_counts_lists(rl, mult, ops.dense_unlisted_resolver(Q, G, r.thr, full_map, g_base), stats=st).cpu().numpy()
+    assert np.array_equal(got_l, want), ("K3 lists", case, cap, st)
     # ---------------- K4 / K6 / K6s
     n = int(rs.randint(1, 1500)); R = int(rs.randint(1, 60))
     data = np.round(rs.normal(40, 3, size=n) * 50) / 50
