@@ -716,6 +716,30 @@ def test_list_mode_bootstrap_equals_bitmask_mode(mmx_mod):
     assert np.array_equal(auto["_bootstrap_values"], ref["_bootstrap_values"])
 
 
+def test_list_mode_at_scale_equals_bitmask_mode(mmx_mod):
+    """Size-independent property at a size where both modes still fit (60 000 queries x 60 000 gallery items, 450 MB of
+    bits): LIST mode with the production capacity returns the bitmask path's bootstrap integers, CIs and base recall;
+    two thirds of the queries have a truncated list and no pair needs the exact recount."""
+    n, d, B = 60_000, 128, 30
+    g = torch.Generator().manual_seed(77)
+    img = torch.randn(n, d, generator=g)
+    img = (img / img.norm(dim=-1, keepdim=True))
+    noise = torch.randn(n, d, generator=g)
+    txt = img + 2.2 * noise / noise.norm(dim=-1, keepdim=True)
+    txt = (txt / txt.norm(dim=-1, keepdim=True)).bfloat16()
+    img = img.bfloat16()
+    q2d = np.arange(n)
+    m_info = {"type": "dense", "name": "DenseSynth-60k"}
+    ref = mmx_mod.run_retrieval_bootstrap(txt, img, q2d, m_info, B, rng=np.random.RandomState(3), list_mode=False)
+    got = mmx_mod.run_retrieval_bootstrap(txt, img, q2d, m_info, B, rng=np.random.RandomState(3), list_mode=True)
+    assert got["_list_mode"] == {"cap": mmx_mod.ops.LIST_CAP, "shards": 1, "unresolved_pairs": 0}
+    assert got["base"] == ref["base"] and 5.0 < ref["base"][1] < 95.0           # a non-trivial ranking problem
+    assert np.array_equal(got["_bootstrap_values"], ref["_bootstrap_values"])
+    for k in (1, 5, 10):
+        for f in ("mean", "lower", "upper", "std"):
+            assert got[f"R@{k}_{f}"] == ref[f"R@{k}_{f}"]
+
+
 def test_run_bootstrap_colpali_small(mmx_mod):
     """ColPali path end to end on a small ragged problem: base metrics and bootstrap integers vs the oracle."""
     n = 40
