@@ -23,6 +23,7 @@ import torch
 
 from . import _lib, ops
 from .failure import (aggregate_failure_analysis, aggregate_failure_from_hits, analyze_query_complexity,
+                      caption_feature_table,
                       get_category_from_caption)
 
 KS = (1, 5, 10)
@@ -424,6 +425,9 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
         done = torch.cuda.Event()
         done.record(main)
         means_d = ops.ci_means_batched(values_d.t().contiguous(), ci_idx)          # nine CIs, one launch
+        # host work that needs no result from the device, done while the device is still busy
+        caps = t2i_captions if t2i_captions is not None else [""] * n_images
+        caption_table = caption_feature_table(caps)
         done.synchronize()
         total_time = time.time() - t0                                                      # main.py:636
         values, means = values_d.cpu().numpy(), means_d.cpu().numpy()
@@ -459,8 +463,10 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     aggregated["Img_per_sec"] = n_images / enc
     if drng is not None:
         drng.commit()
-    caps = t2i_captions if t2i_captions is not None else [""] * n_images
-    aggregated["_failure_analysis"] = aggregate_failure_from_hits(caps, hits, drawn)      # main.py:664
+    if drng is None:
+        caps = t2i_captions if t2i_captions is not None else [""] * n_images
+        caption_table = None
+    aggregated["_failure_analysis"] = aggregate_failure_from_hits(caps, hits, drawn, table=caption_table)  # main.py:664
     aggregated["_bootstrap_values"] = {k: values[:, j].copy() for j, k in enumerate(METRIC_KEYS)}
     aggregated["_base_metrics"] = base_metrics(ranks)
     if tie_report:

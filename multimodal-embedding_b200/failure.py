@@ -73,22 +73,33 @@ def _pct(hits: int, total: int) -> float:
     return 100.0 * hits / total
 
 
+def caption_feature_table(captions: Sequence[str]):
+    """The caption-only half of the failure analysis: (feature masks [3, n] bool, categories, lengths [n]). It does not
+    depend on any score, so the row builder computes it while the GPU is still busy."""
+    raw = [_caption_features(c) for c in captions]
+    n = len(raw)
+    masks = np.empty((len(FEATURES), n), dtype=bool)
+    for fi in range(len(FEATURES)):
+        masks[fi] = np.fromiter((r[fi] for r in raw), dtype=bool, count=n)
+    return masks, [r[4] for r in raw], np.fromiter((r[3] for r in raw), dtype=np.int64, count=n)
+
+
 def aggregate_failure_from_hits(captions: Sequence[str], hits: np.ndarray, drawn: np.ndarray,
-                                first_seen_order: Optional[Sequence[int]] = None) -> Dict[str, Any]:
+                                first_seen_order: Optional[Sequence[int]] = None, table=None) -> Dict[str, Any]:
     """main.py:669-722 evaluated from per-BASE-query totals: ``hits[q]`` = number of (iteration, copy) records of
     query q with correct_r1, ``drawn[q]`` = number of records of query q. Caption features are computed once per base
-    caption. ``first_seen_order`` (query indices in the order the reference's flattened record list first meets them)
-    only fixes the insertion order of ``accuracy_by_category``; default = query order."""
+    caption (``table`` = a precomputed ``caption_feature_table(captions)``). ``first_seen_order`` (query indices in the
+    order the reference's flattened record list first meets them) only fixes the insertion order of
+    ``accuracy_by_category``; default = query order."""
     hits = np.asarray(hits, dtype=np.int64)
     drawn = np.asarray(drawn, dtype=np.int64)
     total = int(drawn.sum())
     if total == 0:
         return {}
-    raw = [_caption_features(c) for c in captions]
-    cats = [r[4] for r in raw]
+    masks, cats, lengths = caption_feature_table(captions) if table is None else table
     analysis: Dict[str, Any] = {"overall_accuracy": _pct(int(hits.sum()), total)}
     for fi, f in enumerate(FEATURES):
-        mask = np.fromiter((r[fi] for r in raw), dtype=bool, count=len(raw))
+        mask = masks[fi]
         if drawn[mask].sum() > 0:
             analysis[f"accuracy_{f}"] = _pct(int(hits[mask].sum()), int(drawn[mask].sum()))
         if drawn[~mask].sum() > 0:
@@ -105,7 +116,6 @@ def aggregate_failure_from_hits(captions: Sequence[str], hits: np.ndarray, drawn
             by_cat_h[c] = by_cat_h.get(c, 0) + int(hits[q])
             by_cat_n[c] += int(drawn[q])
     analysis["accuracy_by_category"] = {c: _pct(h, by_cat_n[c]) for c, h in by_cat_h.items()}
-    lengths = np.fromiter((r[3] for r in raw), dtype=np.int64, count=len(raw))
     for lo, hi in LENGTH_BINS:
         mask = (lengths >= lo) & (lengths <= hi)
         if drawn[mask].sum() > 0:
