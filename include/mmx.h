@@ -190,7 +190,8 @@ int mmx_mt19937_randint(uint32_t* state, uint32_t high, int64_t count, int32_t* 
 int mmx_mt19937_par_scratch_bytes(int n_poly, size_t* bytes);
 /* Optional: positions of the set bits of every polynomial of `polys` (uint16 [n_poly][ld], ld % 4 == 0, rows padded with
  * the value 20592) and their counts (int32 [n_poly]), all device pointers kept by reference; lets the jump convolution
- * gather without scanning bits. Pass NULLs to unregister. Results never depend on it. */
+ * gather without scanning bits. One registration per table pointer (up to 16: short and long tables, several devices);
+ * pass NULL positions to unregister a table. Results never depend on it. */
 int mmx_mt19937_par_set_bit_positions(const uint32_t* polys, const uint16_t* bitpos, const int32_t* bitcnt, int ld);
 /* Test hook: budget = count / acceptance * rel + blocks * 624 raw words (default 1.02, 64). Results never depend on it. */
 int mmx_mt19937_par_set_slack(double rel, double blocks);

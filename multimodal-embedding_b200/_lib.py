@@ -39,6 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     jump-ahead table of K6p (csrc/mt19937_jump_table.npy, ~15 s of host arithmetic once) sits next to it."""
     from . import mtjump
     mtjump.load_table(build_if_missing=True)
+    mtjump.load_table(build_if_missing=True, long=True)
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     deps = srcs + list(CSRC.glob("*.cuh")) + [_PKG.parent / "include" / "mmx.h"]
     if not force and LIB_PATH.exists():

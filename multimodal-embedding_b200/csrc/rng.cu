@@ -439,19 +439,28 @@ extern "C" int mmx_mt19937_par_scratch_bytes(int n_poly, size_t* bytes) {
 
 // Optional accelerator of the jump convolution: the set-bit positions of every polynomial of the table the caller
 // passes as `polys` (uint16 [n_poly][ld], rows padded to a multiple of 4 with the value 33 * 624 = 20592) and their
-// counts. Registered once per process by the binding; results do not depend on it.
-static const uint16_t* g_bitpos = nullptr;
-static const int32_t* g_bitcnt = nullptr;
-static const uint32_t* g_bitpos_polys = nullptr;
-static int g_bitpos_ld = 0;
+// counts. One registration per table (device pointer); results do not depend on it.
+struct BitPosReg {
+    const uint32_t* polys;
+    const uint16_t* bitpos;
+    const int32_t* bitcnt;
+    int ld;
+};
+static BitPosReg g_bitpos_reg[16];  // one entry per (device, table): keyed by the table's device pointer
+static int g_n_bitpos_reg = 0;
 extern "C" int mmx_mt19937_par_set_bit_positions(const uint32_t* polys, const uint16_t* bitpos, const int32_t* bitcnt,
                                                  int ld) {
+    MMX_REQUIRE(polys != nullptr, "polys == NULL");
     MMX_REQUIRE((bitpos == nullptr) == (bitcnt == nullptr) && (bitpos == nullptr || (ld >= 4 && ld % 4 == 0)),
                 "bad bit-position table");
-    g_bitpos_polys = polys;
-    g_bitpos = bitpos;
-    g_bitcnt = bitcnt;
-    g_bitpos_ld = ld;
+    int slot = -1;
+    for (int i = 0; i < g_n_bitpos_reg; ++i)
+        if (g_bitpos_reg[i].polys == polys) slot = i;
+    if (slot < 0) {
+        MMX_REQUIRE(g_n_bitpos_reg < 16, "too many registered jump tables");
+        slot = g_n_bitpos_reg++;
+    }
+    g_bitpos_reg[slot] = BitPosReg{polys, bitpos, bitcnt, ld};
     return 0;
 }
 
@@ -474,10 +483,15 @@ static int par_generate(uint32_t* state, uint32_t rng_incl, int64_t count, int32
     p.state = state;
     p.polys = polys;
     p.seg_blocks = seg_blocks;
-    const bool fast = g_bitpos != nullptr && g_bitpos_polys == polys;
-    p.bitpos = fast ? g_bitpos : nullptr;
-    p.bitcnt = fast ? g_bitcnt : nullptr;
-    p.bitpos_ld = fast ? g_bitpos_ld : 0;
+    p.bitpos = nullptr;
+    p.bitcnt = nullptr;
+    p.bitpos_ld = 0;
+    for (int i = 0; i < g_n_bitpos_reg; ++i)
+        if (g_bitpos_reg[i].polys == polys && g_bitpos_reg[i].bitpos != nullptr) {
+            p.bitpos = g_bitpos_reg[i].bitpos;
+            p.bitcnt = g_bitpos_reg[i].bitcnt;
+            p.bitpos_ld = g_bitpos_reg[i].ld;
+        }
     p.rng = rng_incl;
     p.mask = mask_of(p.rng);
     const size_t smem = ((size_t)(XBLOCKS + 2) * N + XPAD) * 4;

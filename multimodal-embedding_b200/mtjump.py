@@ -24,6 +24,12 @@ SEG_BLOCKS = 64                   # numpy blocks (of 624 raw words) per device s
 SEG_WORDS = N * SEG_BLOCKS
 N_POLY = 295                      # 296 segments per launch = 1.18e7 raw words
 TABLE_PATH = Path(__file__).resolve().parent / "csrc" / "mt19937_jump_table.npy"
+# Long requests (the 9.5e7 draws of a dense model's row, the 1e9 of a 10^6-image bootstrap) take segments of 512 blocks
+# with a second table: the jump convolution costs the same per SEGMENT (~0.3 ms per launch of 296), so 8x longer
+# segments make it 8x cheaper per word (it was 85 % of the launch time at 64 blocks).
+SEG_BLOCKS_LONG = 512
+SEG_WORDS_LONG = N * SEG_BLOCKS_LONG
+TABLE_PATH_LONG = Path(__file__).resolve().parent / "csrc" / "mt19937_jump_table_long.npy"
 
 
 def berlekamp_massey(bits: np.ndarray) -> int:
@@ -125,15 +131,17 @@ def build_table(n_poly: int = N_POLY, seg_words: int = SEG_WORDS) -> np.ndarray:
     return table
 
 
-def load_table(build_if_missing: bool = True) -> np.ndarray:
-    if TABLE_PATH.exists():
-        t = np.load(TABLE_PATH)
+def load_table(build_if_missing: bool = True, long: bool = False) -> np.ndarray:
+    """The table for 64-block segments, or (long=True) for 512-block segments."""
+    path, seg_words = (TABLE_PATH_LONG, SEG_WORDS_LONG) if long else (TABLE_PATH, SEG_WORDS)
+    if path.exists():
+        t = np.load(path)
         if t.shape == (N_POLY, N) and t.dtype == np.uint32:
             return t
     if not build_if_missing:
-        raise FileNotFoundError(TABLE_PATH)
-    t = build_table()
-    np.save(TABLE_PATH, t)
+        raise FileNotFoundError(path)
+    t = build_table(N_POLY, seg_words)
+    np.save(path, t)
     return t
 
 

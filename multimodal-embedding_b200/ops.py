@@ -503,11 +503,16 @@ class DeviceRng:
         host = np.concatenate([np.asarray(st[1], dtype=np.uint32), np.array([st[2]], dtype=np.uint32)])
         self.state = torch.from_numpy(host.view(np.int32).copy()).to(dev)
 
-    def _par_buffers(self):
+    LONG_MIN_WORDS = 24_000_000  # raw words from which the 512-block table pays (two launches of the 64-block one)
+
+    def _par_buffers(self, long: bool = False):
+        """(polys, scratch, positions, counts, seg_blocks) of the jump table for this device: the 64-block table or
+        (long) the 512-block one, uploaded and registered with the library on first use."""
         dev = self.state.device
-        if dev not in DeviceRng._tables:
+        key = (dev, long)
+        if key not in DeviceRng._tables:
             from . import mtjump
-            table = mtjump.load_table(build_if_missing=False)
+            table = mtjump.load_table(build_if_missing=False, long=long)
             polys = torch.from_numpy(table.view(np.int32)).to(dev)
             need = ctypes.c_size_t()
             _lib.check(_lib.lib().mmx_mt19937_par_scratch_bytes(mtjump.N_POLY, ctypes.byref(need)))
@@ -515,11 +520,14 @@ class DeviceRng:
             pos, cnt = mtjump.bit_positions(table)
             pos_d = torch.from_numpy(pos.view(np.int16)).to(dev)
             cnt_d = torch.from_numpy(cnt).to(dev)
-            if len(DeviceRng._tables) == 0:            # the library keeps ONE registration (the first device's)
-                _lib.check(_lib.lib().mmx_mt19937_par_set_bit_positions(polys.data_ptr(), pos_d.data_ptr(),
-                                                                        cnt_d.data_ptr(), pos.shape[1]))
-            DeviceRng._tables[dev] = (polys, torch.empty(need.value, dtype=torch.uint8, device=dev), pos_d, cnt_d)
-        return DeviceRng._tables[dev]
+            _lib.check(_lib.lib().mmx_mt19937_par_set_bit_positions(polys.data_ptr(), pos_d.data_ptr(),
+                                                                    cnt_d.data_ptr(), pos.shape[1]))
+            DeviceRng._tables[key] = (polys, torch.empty(need.value, dtype=torch.uint8, device=dev), pos_d, cnt_d,
+                                      mtjump.SEG_BLOCKS_LONG if long else mtjump.SEG_BLOCKS)
+        return DeviceRng._tables[key]
+
+    def _table_for(self, raw_words: float):
+        return self._par_buffers(long=raw_words >= self.LONG_MIN_WORDS)
 
     def randint(self, high: int, count: int, parallel: Optional[bool] = None) -> torch.Tensor:
         """The next `count` values of ``randint(0, high)``. Large requests use the jump-ahead kernels (K6p, all SMs),
@@ -529,9 +537,10 @@ class DeviceRng:
             parallel = count >= self.PAR_MIN_COUNT
         if parallel:
             from . import mtjump
-            polys, scratch = self._par_buffers()[:2]
+            mask = (1 << max(int(high) - 1, 1).bit_length()) - 1                   # numpy's masked rejection
+            polys, scratch, _, _, seg_blocks = self._table_for(count * (mask + 1.0) / float(high))
             _lib.check(_lib.lib().mmx_mt19937_randint_par(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
-                                                          polys.data_ptr(), mtjump.N_POLY, mtjump.SEG_BLOCKS,
+                                                          polys.data_ptr(), mtjump.N_POLY, seg_blocks,
                                                           scratch.data_ptr(), scratch.numel(), _stream()))
         else:
             _lib.check(_lib.lib().mmx_mt19937_randint(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
@@ -542,20 +551,20 @@ class DeviceRng:
         """The next `count` raw 32-bit outputs (as int32 bit patterns). advance=False leaves the generator where it
         is (the draws are made from a copy of the state); ``skip`` then moves it by the number actually consumed."""
         from . import mtjump
-        polys, scratch = self._par_buffers()[:2]
+        polys, scratch, _, _, seg_blocks = self._table_for(count)
         st = self.state if advance else self.state.clone()
         out = torch.empty((count,), dtype=torch.int32, device=self.state.device)
         _lib.check(_lib.lib().mmx_mt19937_raw_par(st.data_ptr(), int(count), out.data_ptr(), polys.data_ptr(),
-                                                  mtjump.N_POLY, mtjump.SEG_BLOCKS, scratch.data_ptr(),
+                                                  mtjump.N_POLY, seg_blocks, scratch.data_ptr(),
                                                   scratch.numel(), _stream()))
         return out
 
     def skip(self, count: int) -> None:
         """Advance the generator by `count` raw words without materialising them."""
         from . import mtjump
-        polys, scratch = self._par_buffers()[:2]
+        polys, scratch, _, _, seg_blocks = self._table_for(count)
         _lib.check(_lib.lib().mmx_mt19937_raw_par(self.state.data_ptr(), int(count), None, polys.data_ptr(),
-                                                  mtjump.N_POLY, mtjump.SEG_BLOCKS, scratch.data_ptr(),
+                                                  mtjump.N_POLY, seg_blocks, scratch.data_ptr(),
                                                   scratch.numel(), _stream()))
 
     def shuffle_indices(self, n: int, n_shuffles: int) -> torch.Tensor:

@@ -543,9 +543,9 @@ def test_device_rng_jump_ahead_without_position_table(mmx_mod):
     path gives the same stream."""
     h = mmx_mod._lib.lib()
     d = mmx_mod.ops.DeviceRng(np.random.RandomState(11))
-    polys, _, pos_d, cnt_d = d._par_buffers()
+    polys, _, pos_d, cnt_d, _ = d._par_buffers()
     try:
-        mmx_mod._lib.check(h.mmx_mt19937_par_set_bit_positions(None, None, None, 0))
+        mmx_mod._lib.check(h.mmx_mt19937_par_set_bit_positions(polys.data_ptr(), None, None, 0))
         got = d.randint(5000, 3_000_000, parallel=True).cpu().numpy()
     finally:
         mmx_mod._lib.check(h.mmx_mt19937_par_set_bit_positions(polys.data_ptr(), pos_d.data_ptr(), cnt_d.data_ptr(),
@@ -554,6 +554,30 @@ def test_device_rng_jump_ahead_without_position_table(mmx_mod):
     rs = np.random.RandomState(11)
     assert np.array_equal(got.astype(np.int64), rs.randint(0, 5000, size=3_000_000))
     assert np.array_equal(again.astype(np.int64), rs.randint(0, 5000, size=1_000_000))
+
+
+def test_device_rng_long_requests_take_the_512_block_table(mmx_mod):
+    """Requests above DeviceRng.LONG_MIN_WORDS raw words use the second jump table (512-block segments: the jump
+    convolution is paid once per segment). Same stream bit for bit: a long masked-rejection request, a short one
+    after it (64-block table), a long raw-word skip, and numpy's generator ends in the same state."""
+    rs_dev, rs_ref = np.random.RandomState(77), np.random.RandomState(77)
+    rs_dev.randint(0, 9, size=1234)
+    rs_ref.randint(0, 9, size=1234)                                     # start somewhere inside a block
+    d = mmx_mod.ops.DeviceRng(rs_dev)
+    n_long = 33_000_000                                                 # x 8192/5000 = 5.4e7 raw words: long table
+    assert n_long * 8192 / 5000 >= d.LONG_MIN_WORDS
+    a = d.randint(5000, n_long).cpu().numpy()
+    want = rs_ref.randint(0, 5000, size=n_long)
+    assert np.array_equal(a, want.astype(np.int32))
+    del a, want
+    b = d.randint(1000, 700_000).cpu().numpy()                          # short request: the 64-block table
+    assert np.array_equal(b, rs_ref.randint(0, 1000, size=700_000).astype(np.int32))
+    d.skip(40_000_001)                                                  # long table again, raw words, odd count
+    rs_ref._bit_generator.random_raw(40_000_001)
+    c = d.randint(1 << 20, 300_000).cpu().numpy()
+    assert np.array_equal(c, rs_ref.randint(0, 1 << 20, size=300_000).astype(np.int32))
+    d.commit()
+    assert rs_dev.randint(0, 1 << 30, size=5).tolist() == rs_ref.randint(0, 1 << 30, size=5).tolist()
 
 
 def test_device_rng_global_stream_and_host_mode_agree(mmx_mod, golden_dir, monkeypatch):

@@ -45,3 +45,18 @@ def test_table_rows_are_powers():
     assert np.array_equal(t[0], mtjump.poly_to_words(g1))
     k = mtjump.N_POLY
     assert np.array_equal(t[k - 1], mtjump.poly_to_words(mtjump.pow_x(k * mtjump.SEG_WORDS, phi)))
+
+
+def test_long_table_rows_are_powers_and_jump():
+    """The 512-block table (long requests): first and last rows are the right powers of x, and a jump with row 2 lands
+    on numpy's key after 2 x 512 regenerations."""
+    t = mtjump.load_table(long=True)
+    assert t.shape == (mtjump.N_POLY, mtjump.N) and t.dtype == np.uint32
+    phi = mtjump.characteristic_polynomial()
+    assert np.array_equal(t[0], mtjump.poly_to_words(mtjump.pow_x(mtjump.SEG_WORDS_LONG, phi)))
+    k = mtjump.N_POLY
+    assert np.array_equal(t[k - 1], mtjump.poly_to_words(mtjump.pow_x(k * mtjump.SEG_WORDS_LONG, phi)))
+    key = np.asarray(np.random.RandomState(9).get_state()[1], dtype=np.uint32)
+    got = mtjump.jump_key(key, t[1])
+    want = _key_after_blocks(9, 2 * mtjump.SEG_BLOCKS_LONG)
+    assert np.array_equal(got[1:], want[1:]) and (got[0] ^ want[0]) & np.uint32(0x80000000) == 0
