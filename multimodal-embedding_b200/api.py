@@ -420,7 +420,7 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
         for t in (sample_indices, ci_idx):
             t.record_stream(main)
         correct_d, hits_d, drawn_d = _bootstrap_counts_device(ranks, sample_indices, n_images, want_hits=True)
-        n_t = torch.tensor(float(n_images), dtype=torch.float64, device=dev)
+        n_t = torch.full((), float(n_images), dtype=torch.float64, device=dev)   # a fill kernel, not a blocking host copy
         values_d = 100.0 * correct_d.to(torch.float64) / n_t          # tensor / tensor: IEEE division, as numpy's
         done = torch.cuda.Event()
         done.record(main)

@@ -73,15 +73,29 @@ def _pct(hits: int, total: int) -> float:
     return 100.0 * hits / total
 
 
+_TABLE_CACHE: Dict[Any, Any] = {}
+
+
 def caption_feature_table(captions: Sequence[str]):
     """The caption-only half of the failure analysis: (feature masks [3, n] bool, categories, lengths [n]). It does not
-    depend on any score, so the row builder computes it while the GPU is still busy."""
-    raw = [_caption_features(c) for c in captions]
+    depend on any score, so the row builder computes it while the GPU is still busy; every model of a benchmark run sees
+    the same caption list, so the last few tables are kept (keyed by the captions themselves)."""
+    key = tuple(captions)
+    hit = _TABLE_CACHE.get(key)
+    if hit is not None:
+        return hit
+    raw = [_caption_features(c) for c in key]
     n = len(raw)
-    masks = np.empty((len(FEATURES), n), dtype=bool)
-    for fi in range(len(FEATURES)):
-        masks[fi] = np.fromiter((r[fi] for r in raw), dtype=bool, count=n)
-    return masks, [r[4] for r in raw], np.fromiter((r[3] for r in raw), dtype=np.int64, count=n)
+    if n:
+        spatial, color, counting, length, cats = zip(*raw)
+        masks = np.array([spatial, color, counting], dtype=bool)
+        table = (masks, list(cats), np.array(length, dtype=np.int64))
+    else:
+        table = (np.zeros((len(FEATURES), 0), dtype=bool), [], np.zeros(0, dtype=np.int64))
+    if len(_TABLE_CACHE) >= 8:
+        _TABLE_CACHE.pop(next(iter(_TABLE_CACHE)))
+    _TABLE_CACHE[key] = table
+    return table
 
 
 def aggregate_failure_from_hits(captions: Sequence[str], hits: np.ndarray, drawn: np.ndarray,

@@ -71,8 +71,7 @@ class ProtocolRanks:
         """100.0 * correct / n exactly as main.py:358 (python float arithmetic on integer counts)."""
         cnt = self.cnt_above
         n = self.nq
-        ks = torch.tensor([1, 5, 10], device=cnt.device)
-        correct = (cnt[None, :] < ks[:, None]).sum(dim=1).tolist()
+        correct = torch.stack([(cnt < k).sum() for k in (1, 5, 10)]).tolist()      # one device->host read, no upload
         return {k: 100.0 * c / n for k, c in zip((1, 5, 10), correct)}
 
 
