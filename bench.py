@@ -438,6 +438,20 @@ def dense_section(dev, K, W, cpu_iters=2):
     e1.record()
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1) / K
+    # K1 on its own: the ranking (COUNT) pass of the I2T protocol, 5000 x 25000 x 1152, against the bf16 peak
+    gt_off = torch.arange(0, 5 * N + 1, 5, dtype=torch.int32, device=dev)
+    gt_idx = torch.arange(5 * N, dtype=torch.int32, device=dev)
+    thr = ops.dense_rank(img_d, all_d, gt_off, gt_idx, threshold_only=True).thr
+    for _ in range(3):
+        ops.dense_rank(img_d, all_d, gt_off, gt_idx, thr=thr)
+    k1_iters = 20
+    e0.record()
+    for _ in range(k1_iters):
+        ops.dense_rank(img_d, all_d, gt_off, gt_idx, thr=thr)
+    e1.record()
+    torch.cuda.synchronize()
+    k1_ms = e0.elapsed_time(e1) / k1_iters
+    k1_tf = 2.0 * N * 5 * N * Dm / (k1_ms * 1e-3) / 1e12
     # end to end through the reference-signature API, host tensors in, CSV row out (host RNG included)
     imgp, t2ip, allp = img.pin_memory(), t2i.pin_memory(), all_txt.pin_memory()
     mmx.run_bootstrap_from_embeddings(imgp, t2ip, allp, m_info, N_ITER, rng=np.random.RandomState(42))
@@ -478,6 +492,9 @@ def dense_section(dev, K, W, cpu_iters=2):
     return {"cpu_baseline": cpu, "workload": "SigLIP-400M dense scoring 5000x1152 / 25000x1152, T2I + I2T(1-to-5) + I2T_Sym, "
                         "1000-iter bootstrap + 9 CIs (10 000 resamples each)",
             "metric": "dense_score_rank_bootstrap_wall_ms", "device_resident_ms": dev_ms, "e2e_ms": e2e_ms,
+            "k1_count_pass": {"shape": "5000 x 25000 x 1152 (I2T ranking pass, bitmask written)", "ms": k1_ms,
+                              "tflops": k1_tf, "frac_of_bf16_peak": k1_tf / peaks()["bf16"],
+                              "note": f"{k1_iters} back-to-back launches incl. the host-side allocation of their outputs"},
             "e2e_note": "mmx.run_bootstrap_from_embeddings from pinned host tensors to the 42-column row; the "
                         "~9.5e7 numpy MT19937 draws are regenerated on the device (K6)", "permutation_test_ms": perm_ms,
             "permutation_p": float(p), "pairs_scored": pairs,
