@@ -504,8 +504,9 @@ def dense_section(dev, K, W, cpu_iters=2):
 
 def emit(line: dict) -> None:
     """The ONE JSON line goes to the process's original stdout."""
-    _JSON_OUT.write(json.dumps(line) + "\n")
-    _JSON_OUT.flush()
+    out = globals().get("_JSON_OUT") or sys.stdout          # imported as a module: plain stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 if __name__ == "__main__":
