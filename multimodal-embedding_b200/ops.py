@@ -491,7 +491,7 @@ class DeviceRng:
     into the numpy object, so the host stream continues as if numpy itself had made the draws."""
 
     PAR_MIN_COUNT = 200_000      # below this one small CTA (K6) is as fast as the jump-ahead launch sequence (K6p)
-    _tables: dict = {}           # device -> (polys tensor, scratch tensor)
+    _tables: dict = {}           # (device, long) -> (polys, scratch, bit positions, bit counts, seg_blocks)
 
     def __init__(self, source, device: Optional[torch.device] = None):
         self.source = np.random if source is None else source
