@@ -43,6 +43,15 @@ def test_failure_analysis_matches_reference_golden(golden_dir):
     for c in caps[:5]:
         assert mmx.analyze_query_complexity(c) == oracle.metrics.analyze_query_complexity(c)
         assert mmx.get_category_from_caption(c) == oracle.metrics.get_category_from_caption(c)
+    # the caption-only half precomputed (what the row builder does while the GPU is busy) and its small cache
+    table = mmx.failure.caption_feature_table(caps)
+    assert mmx.failure.caption_feature_table(list(caps)) is table                       # same captions: cached
+    got3 = mmx.failure.aggregate_failure_from_hits(caps, hits, np.ones(len(caps), dtype=np.int64), table=table)
+    assert json.loads(json.dumps(got3, sort_keys=True)) == want
+    for k in range(12):                                                                 # the cache keeps the last few
+        mmx.failure.caption_feature_table([f"a dog {k}"])
+    assert len(mmx.failure._TABLE_CACHE) <= 8
+    assert mmx.failure.caption_feature_table([]) [2].shape == (0,)
 
 
 def test_pad_flags_and_flatten():
