@@ -33,12 +33,16 @@ constexpr int L = 32768;       // words per chunk (accept counts fit uint16)
 constexpr int CT = 512;        // threads of a table CTA
 constexpr int RW = 512;        // words per round (simulate, then compact)
 constexpr int PB = 64;         // permutations per composition block
-constexpr int MAX_N = 16384;   // work grows with n * |W| (~n^2 P); beyond this the host replays the shuffles
+constexpr int MAX_N = 16384;   // B/C/D: work grows with n * |W| (~n^2 P); longer arrays take the LONG emit below
+constexpr int MAX_N_LONG = 65536;   // LONG emit: masked values fit uint16
+constexpr int LT = 1024;            // threads of the LONG emit CTA
+constexpr int LW_MAX = 65536;       // words of one mask epoch's window (uint16 values + one flag byte each: 192 KB)
 
 struct Plan {
     long long n_chunks, steps;
     int n_blocks;
-    size_t off_tab, off_m, off_s, off_j, off_arr, off_pi, off_c, off_d, total;
+    bool long_n;
+    size_t off_tab, off_m, off_s, off_j, off_arr, off_pi, off_c, off_d, off_g, total;
 };
 
 static Plan make_plan(int n, int P, long long n_words) {
@@ -47,8 +51,9 @@ static Plan make_plan(int n, int P, long long n_words) {
     pl.n_chunks = (n_words + L - 1) / L;
     pl.steps = (long long)P * (n - 1);
     pl.n_blocks = (P + PB - 1) / PB;
+    pl.long_n = n > MAX_N;
     size_t o = 256;
-    pl.off_tab = o; o += up((size_t)pl.n_chunks * (n - 1) * 2);   // uint16 accepts per (chunk, start state)
+    pl.off_tab = o; o += up(pl.long_n ? 0 : (size_t)pl.n_chunks * (n - 1) * 2);   // uint16 accepts per (chunk, start state)
     pl.off_m = o;   o += up((size_t)(pl.n_chunks + 1) * 4);       // start state of every chunk
     pl.off_s = o;   o += up((size_t)(pl.n_chunks + 1) * 8);       // global step offset of every chunk
     pl.off_j = o;   o += up((size_t)pl.steps * 4);                // j of every step
@@ -56,6 +61,7 @@ static Plan make_plan(int n, int P, long long n_words) {
     pl.off_pi = o;  o += up((size_t)n * P * 4);                   // [P][n] pi_p
     pl.off_c = o;   o += up((size_t)pl.n_blocks * n * 4);         // block composites
     pl.off_d = o;   o += up((size_t)(pl.n_blocks + 1) * n * 4);   // prefixes of the block composites
+    pl.off_g = o;   o += up(pl.long_n ? (size_t)(pl.n_blocks + 1) * 2 * n * 4 : 0);   // LONG: composition buffers in L2
     pl.total = o;
     return pl;
 }
@@ -220,6 +226,168 @@ emit_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, long 
     }
 }
 
+// D-long: the accepted j values of P cumulative shuffles of an array too long for the table scheme (n > MAX_N), by ONE
+// CTA that is parallel WITHIN a permutation (prototype and proof of exactness against numpy: dev/proto_long_shuffle.py).
+// Inside a mask epoch (all steps i with the same mask M, i from i_hi down to i_lo) the k-th accepted word serves step
+// i_hi - k, so word t is accepted iff  v_t <= i_hi - a(t),  v_t = word_t & M,  a(t) = accepts before t. a(t) is the
+// only serial quantity; it is bracketed, L(t) <= a(t) <= U(t), and the brackets are tightened round by round:
+//     surely accepted  v_t <= i_hi - U(t)        surely rejected  v_t > i_hi - L(t)
+//     L'(t) = surely accepted words before t     U'(t) = words before t that are not surely rejected
+// — two block-wide prefix sums per round, every round exact, 4-8 rounds until L = U up to the epoch's last accept.
+// Every thread owns a contiguous segment of the epoch's window (values and one flag byte per word in shared memory).
+struct LongScan {
+    int baseA, baseU, totA, totU;
+};
+__device__ __forceinline__ LongScan long_block_scan(int a, int u, int* wA, int* wU, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    int ia = a, iu = u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tu = __shfl_up_sync(0xffffffffu, iu, o);
+        if (lane >= o) {
+            ia += ta;
+            iu += tu;
+        }
+    }
+    __syncthreads();  // the previous use of wA / wU is over
+    if (lane == 31) {
+        wA[warp] = ia;
+        wU[warp] = iu;
+    }
+    __syncthreads();
+    int pa = 0, pu = 0, sa = 0, su = 0;
+#pragma unroll
+    for (int w = 0; w < LT / 32; ++w) {
+        const int ca = wA[w], cu = wU[w];
+        if (w < warp) {
+            pa += ca;
+            pu += cu;
+        }
+        sa += ca;
+        su += cu;
+    }
+    LongScan r;
+    r.baseA = pa + ia - a;
+    r.baseU = pu + iu - u;
+    r.totA = sa;
+    r.totU = su;
+    return r;
+}
+
+__global__ void __launch_bounds__(LT)
+emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, int P, long long* __restrict__ info,
+                 int32_t* __restrict__ jout) {
+    extern __shared__ uint8_t lsm[];
+    uint16_t* sv = reinterpret_cast<uint16_t*>(lsm);  // [LW_MAX] masked values of the window
+    uint8_t* sf = lsm + (size_t)LW_MAX * 2;           // [LW_MAX] bit 0 = surely accepted, bit 1 = surely rejected
+    __shared__ int wA[LT / 32], wU[LT / 32];
+    __shared__ int s_done_at, s_conv;
+    const int tid = threadIdx.x;
+    long long pos = 0, step_base = 0;
+    for (int p = 0; p < P; ++p, step_base += n - 1) {
+        int i_hi = n - 1;
+        while (i_hi >= 1) {
+            const int b = 32 - __clz(i_hi);
+            const uint32_t M = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
+            const int i_lo = max(1 << (b - 1), 1);
+            const int c = i_hi - i_lo + 1;
+            int W = min(LW_MAX, (int)(1.40f * (float)c) + 1024);
+            bool epoch_done = false;
+            while (!epoch_done) {
+                if (pos + W > n_words) W = (int)(n_words - pos);
+                if (W < c) {  // the stream is too short: the caller retries with more words
+                    if (tid == 0) {
+                        info[0] = -1;
+                        info[1] = -1;
+                    }
+                    return;
+                }
+                __syncthreads();  // everybody is done with the previous window
+                for (int t = tid; t < W; t += LT) {
+                    const uint32_t v = words[pos + t] & M;
+                    sv[t] = (uint16_t)v;
+                    sf[t] = (v <= (uint32_t)i_hi) ? 0 : 2;  // a(t) >= 0: a word above i_hi is never accepted
+                }
+                __syncthreads();
+                const int S = (W + LT - 1) / LT;
+                const int t0 = min(W, tid * S), t1 = min(W, t0 + S);
+                int prevA = -1, prevU = -1;
+                for (int round = 0;; ++round) {
+                    // ---- counts of the current flags, their block-wide exclusive prefixes
+                    int a = 0, u = 0;
+                    for (int t = t0; t < t1; ++t) {
+                        const int f = sf[t];
+                        a += f & 1;
+                        u += (f >> 1) ^ 1;
+                    }
+                    const LongScan sc = long_block_scan(a, u, wA, wU, tid);
+                    if (tid == 0) s_done_at = -1;
+                    __syncthreads();
+                    // ---- the thread whose segment holds the c-th sure accept: is everything before it settled?
+                    if (sc.baseA < c && sc.baseA + a >= c) {
+                        int ra = sc.baseA, ru = sc.baseU;
+                        for (int t = t0; t < t1; ++t) {
+                            const int f = sf[t];
+                            ra += f & 1;
+                            ru += (f >> 1) ^ 1;
+                            if (ra == c) {
+                                s_done_at = t;
+                                s_conv = (ru == c) ? 1 : 0;  // U = L up to and including the last accept
+                                break;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                    const int done_at = s_done_at;
+                    if (done_at >= 0 && s_conv) {
+                        // ---- emit: the k-th accepted word of the epoch is the j of step i_hi - k
+                        int ra = sc.baseA;
+                        int32_t* out = jout + step_base + (n - 1 - i_hi);
+                        for (int t = t0; t < t1 && ra < c; ++t)
+                            if (sf[t] & 1) out[ra++] = (int32_t)sv[t];
+                        pos += done_at + 1;
+                        epoch_done = true;
+                        break;
+                    }
+                    if (sc.totA == prevA && sc.totU == prevU) {
+                        // no flag changed in the last round and the c-th accept is not settled: the window is too short
+                        if (W >= LW_MAX || pos + W >= n_words) {
+                            if (tid == 0) {
+                                info[0] = -1;
+                                info[1] = (W >= LW_MAX) ? -3 : -1;
+                            }
+                            return;
+                        }
+                        W = min(LW_MAX, 2 * W);
+                        break;  // restage a longer window of the same epoch
+                    }
+                    prevA = sc.totA;
+                    prevU = sc.totU;
+                    // ---- tighten: new flags from the brackets L(t) = ra, U(t) = ru of the OLD flags
+                    {
+                        int ra = sc.baseA, ru = sc.baseU;
+                        for (int t = t0; t < t1; ++t) {
+                            const int f = sf[t];
+                            const int v = sv[t];
+                            const int nf = (v <= i_hi - ru ? 1 : 0) | (v > i_hi - ra ? 2 : 0);
+                            ra += f & 1;
+                            ru += (f >> 1) ^ 1;
+                            sf[t] = (uint8_t)nf;
+                        }
+                    }
+                    // each thread rewrote only its own segment; the next round's scan synchronises before any
+                    // cross-thread read
+                }
+            }
+            i_hi = i_lo - 1;
+        }
+    }
+    if (tid == 0) {
+        info[0] = 0;
+        info[1] = pos;  // exactly this many words were consumed
+    }
+}
+
 // E: thread p applies the swaps of permutation p to an identity array held as column p of arr[i][P]
 __global__ void __launch_bounds__(128)
 apply_kernel(const int32_t* __restrict__ jout, int n, int P, const long long* __restrict__ info,
@@ -253,11 +421,12 @@ transpose_kernel(const int32_t* __restrict__ src, int n, int P, int32_t* __restr
 // write_rows = 1 stores every intermediate row (the result), 0 stores only the block composite.
 __global__ void __launch_bounds__(512)
 compose_block_kernel(const int32_t* __restrict__ pi, int n, int P, const int32_t* __restrict__ start,
-                     int32_t* __restrict__ comp_out, int32_t* __restrict__ rows_out) {
+                     int32_t* __restrict__ comp_out, int32_t* __restrict__ rows_out, int32_t* gbuf) {
     extern __shared__ int32_t sm[];
-    int32_t* cur = sm;
-    int32_t* nxt = sm + n;
     const int b = blockIdx.x;
+    // long arrays (n > MAX_N) keep the two working rows in L2 (gbuf: 2 n words per block) instead of shared memory
+    int32_t* cur = gbuf != nullptr ? gbuf + (size_t)b * 2 * n : sm;
+    int32_t* nxt = cur + n;
     for (int k = threadIdx.x; k < n; k += blockDim.x) cur[k] = start != nullptr ? start[(long long)b * n + k] : k;
     __syncthreads();
     const int p_end = min(P, (b + 1) * PB);
@@ -279,10 +448,11 @@ compose_block_kernel(const int32_t* __restrict__ pi, int n, int P, const int32_t
 
 // F2: prefix[b] = state before block b (prefix[0] = identity, prefix[b+1] = prefix[b] o comp[b])
 __global__ void __launch_bounds__(512)
-compose_scan_kernel(const int32_t* __restrict__ comp, int n, int n_blocks, int32_t* __restrict__ prefix) {
+compose_scan_kernel(const int32_t* __restrict__ comp, int n, int n_blocks, int32_t* __restrict__ prefix,
+                    int32_t* gbuf) {
     extern __shared__ int32_t sm[];
-    int32_t* cur = sm;
-    int32_t* nxt = sm + n;
+    int32_t* cur = gbuf != nullptr ? gbuf : sm;
+    int32_t* nxt = cur + n;
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         cur[k] = k;
         prefix[k] = k;
@@ -309,7 +479,8 @@ using namespace mmx;
 using namespace mmx::shuf;
 
 extern "C" int mmx_perm_shuffle_workspace_bytes(int n, int P, int64_t n_words, size_t* bytes) {
-    MMX_REQUIRE(bytes != nullptr && n >= 2 && n <= MAX_N && P >= 1 && n_words >= 1, "bad argument (2 <= n <= %d)", MAX_N);
+    MMX_REQUIRE(bytes != nullptr && n >= 2 && n <= MAX_N_LONG && P >= 1 && n_words >= 1, "bad argument (2 <= n <= %d)",
+                MAX_N_LONG);
     *bytes = make_plan(n, P, n_words).total;
     return 0;
 }
@@ -317,7 +488,7 @@ extern "C" int mmx_perm_shuffle_workspace_bytes(int n, int P, int64_t n_words, s
 extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, int P, int32_t* perm, int64_t* info,
                                 void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     MMX_REQUIRE(words != nullptr && perm != nullptr && info != nullptr && workspace != nullptr, "NULL argument");
-    MMX_REQUIRE(n >= 2 && n <= MAX_N && P >= 1 && n_words >= 1, "bad argument (2 <= n <= %d)", MAX_N);
+    MMX_REQUIRE(n >= 2 && n <= MAX_N_LONG && P >= 1 && n_words >= 1, "bad argument (2 <= n <= %d)", MAX_N_LONG);
     const Plan pl = make_plan(n, P, n_words);
     MMX_REQUIRE(workspace_bytes >= pl.total, "workspace too small: need %zu bytes", pl.total);
     MMX_REQUIRE(pl.n_chunks < (1ll << 31), "too many chunks");
@@ -330,35 +501,48 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
     int32_t* pi = reinterpret_cast<int32_t*>(ws + pl.off_pi - 256);
     int32_t* comp = reinterpret_cast<int32_t*>(ws + pl.off_c - 256);
     int32_t* prefix = reinterpret_cast<int32_t*>(ws + pl.off_d - 256);
+    int32_t* gbuf = pl.long_n ? reinterpret_cast<int32_t*>(ws + pl.off_g - 256) : nullptr;
     const int n1 = n - 1;
-    const size_t smem_tab = (size_t)(RW + CT) * 4 + 3 * (size_t)((n1 + 1) & ~1) * 2;
-    static const char tab_attr_tag = 0;
-    if (first_use_on_device(&tab_attr_tag)) {
-        MMX_CHECK_CUDA(cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (RW + CT) * 4 + 3 * MAX_N * 2));
+    if (pl.long_n) {
+        // n > MAX_N: one CTA, parallel within a permutation (bracketing prefix sums per mask epoch)
+        const size_t smem_long = (size_t)LW_MAX * 3;
+        static const char long_attr_tag = 0;
+        if (first_use_on_device(&long_attr_tag))
+            MMX_CHECK_CUDA(cudaFuncSetAttribute(emit_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem_long));
+        emit_long_kernel<<<1, LT, smem_long, stream>>>(words, n_words, n, P, reinterpret_cast<long long*>(info), jout);
+        MMX_CHECK_CUDA(cudaGetLastError());
+    } else {
+        const size_t smem_tab = (size_t)(RW + CT) * 4 + 3 * (size_t)((n1 + 1) & ~1) * 2;
+        static const char tab_attr_tag = 0;
+        if (first_use_on_device(&tab_attr_tag)) {
+            MMX_CHECK_CUDA(cudaFuncSetAttribute(tables_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (RW + CT) * 4 + 3 * MAX_N * 2));
+        }
+        tables_kernel<<<(unsigned)pl.n_chunks, CT, smem_tab, stream>>>(words, n_words, n1, tab);
+        MMX_CHECK_CUDA(cudaGetLastError());
+        chain_kernel<<<1, 32, 0, stream>>>(tab, pl.n_chunks, n1, pl.steps, start_m, start_s,
+                                           reinterpret_cast<long long*>(info));
+        emit_kernel<<<(unsigned)pl.n_chunks, 32, 0, stream>>>(words, n_words, n1, pl.steps, start_m, start_s,
+                                                              reinterpret_cast<long long*>(info), jout);
+        MMX_CHECK_CUDA(cudaGetLastError());
     }
-    tables_kernel<<<(unsigned)pl.n_chunks, CT, smem_tab, stream>>>(words, n_words, n1, tab);
-    MMX_CHECK_CUDA(cudaGetLastError());
-    chain_kernel<<<1, 32, 0, stream>>>(tab, pl.n_chunks, n1, pl.steps, start_m, start_s,
-                                       reinterpret_cast<long long*>(info));
-    emit_kernel<<<(unsigned)pl.n_chunks, 32, 0, stream>>>(words, n_words, n1, pl.steps, start_m, start_s,
-                                                                       reinterpret_cast<long long*>(info), jout);
-    MMX_CHECK_CUDA(cudaGetLastError());
     // when the words did not suffice (info[1] = -1) the swaps are skipped and the stages below shuffle unspecified
     // but in-range index rows; the caller checks info[1] before using `perm` and retries with a longer stream
     MMX_CHECK_CUDA(cudaMemsetAsync(arr, 0, (size_t)n * P * 4, stream));
     apply_kernel<<<(P + 127) / 128, 128, 0, stream>>>(jout, n, P, reinterpret_cast<const long long*>(info), arr);
     dim3 gt((unsigned)((P + 31) / 32), (unsigned)((n + 31) / 32));
     transpose_kernel<<<gt, 256, 0, stream>>>(arr, n, P, pi);
-    const size_t smem = (size_t)n * 8;
+    const size_t smem = pl.long_n ? 0 : (size_t)n * 8;
     static const char attr_set_tag = 0;
     if (first_use_on_device(&attr_set_tag)) {
         MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_N * 8));
         MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_N * 8));
     }
-    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, nullptr, comp, nullptr);
-    compose_scan_kernel<<<1, 512, smem, stream>>>(comp, n, pl.n_blocks, prefix);
-    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, prefix, nullptr, perm);
+    int32_t* gscan = pl.long_n ? gbuf + (size_t)pl.n_blocks * 2 * n : nullptr;
+    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, nullptr, comp, nullptr, gbuf);
+    compose_scan_kernel<<<1, 512, smem, stream>>>(comp, n, pl.n_blocks, prefix, gscan);
+    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, prefix, nullptr, perm, gbuf);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

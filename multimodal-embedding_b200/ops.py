@@ -589,6 +589,8 @@ class DeviceRng:
             consumed = int(info[1].item())
             if consumed >= 0:
                 break
+            if consumed == -3:
+                raise _lib.MmxError("shuffle replay: a mask epoch did not fit the 65 536-word window")
             n_words = int(n_words * 1.25)          # 8 sigma was not enough: replay with a longer stream
         self.skip(consumed)
         return perm

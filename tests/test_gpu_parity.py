@@ -528,6 +528,39 @@ def test_device_shuffle_reports_short_stream(mmx_mod):
                           np.random.RandomState(1)._bit_generator.random_raw(n_words).astype(np.uint32))
 
 
+@pytest.mark.parametrize("n,n_shuffles", [(16385, 5), (20011, 7), (50000, 3), (65536, 2)])
+def test_device_shuffle_long_arrays_match_numpy(mmx_mod, n, n_shuffles):
+    """Arrays beyond the table scheme's 16 384 elements: the LONG emit kernel (one CTA, parallel within a permutation:
+    bracketing prefix sums per mask epoch; numpy prototype dev/proto_long_shuffle.py) gives numpy's cumulative shuffles
+    and leaves the generator where numpy's own shuffle calls leave it."""
+    rs_dev, rs_ref = np.random.RandomState(n), np.random.RandomState(n)
+    rs_dev.randint(0, 100, size=333)
+    rs_ref.randint(0, 100, size=333)
+    d = mmx_mod.ops.DeviceRng(rs_dev)
+    perm = d.shuffle_indices(n, n_shuffles).cpu().numpy()
+    d.commit()
+    ix = np.arange(n)
+    for p_ in range(n_shuffles):
+        rs_ref.shuffle(ix)
+        assert np.array_equal(perm[p_], ix), (n, p_)
+    assert rs_dev.randint(0, 1 << 30, size=4).tolist() == rs_ref.randint(0, 1 << 30, size=4).tolist()
+
+
+def test_permutation_test_long_arrays_on_the_device(mmx_mod, monkeypatch):
+    """permutation_test on 9 000 + 9 000 values with the device shuffles enabled for long arrays == the host-shuffle
+    path == the oracle (same p-value, same generator state)."""
+    rs = np.random.RandomState(4)
+    d1, d2 = rs.normal(size=9000), rs.normal(0.02, 1.0, size=9000)
+    monkeypatch.setattr(mmx_mod.api, "DEVICE_SHUFFLE_MAX_N", 16384)
+    g_host = np.random.RandomState(8)
+    p_host = mmx_mod.permutation_test(d1, d2, 40, rng=g_host)
+    monkeypatch.setattr(mmx_mod.api, "DEVICE_SHUFFLE_MAX_N", 65536)
+    g_dev = np.random.RandomState(8)
+    p_dev = mmx_mod.permutation_test(d1, d2, 40, rng=g_dev)
+    assert p_host == p_dev == oracle.permutation_test(d1, d2, 40, rng=np.random.RandomState(8))
+    assert g_host.randint(0, 1 << 30) == g_dev.randint(0, 1 << 30)
+
+
 def test_permutation_test_long_arrays_fall_back_to_host_shuffles(mmx_mod, monkeypatch):
     monkeypatch.setattr(mmx_mod.api, "DEVICE_SHUFFLE_MAX_N", 100)
     rs = np.random.RandomState(3)
