@@ -208,7 +208,9 @@ int mmx_mt19937_raw_par(uint32_t* state, int64_t count, uint32_t* out, const uin
  * j = random_interval(i) by masked rejection). words uint32 [n_words] = mmx_mt19937_raw_par output from the current
  * state; perm int32 [P, n] = the index array after every shuffle (what mmx_perm_stats takes);
  * info int64 [2] (device): info[1] = number of words the P shuffles consumed, or -1 when n_words was too small (perm
- * is then unspecified; call again with more words). 2 <= n <= 16384 (the table stage grows with n^2 * P).
+ * is then unspecified; call again with more words; -3: a mask epoch did not fit the 65 536-word window, which needs a
+ * > 100-sigma run of rejections). 2 <= n <= 65536: up to 16 384 elements the table scheme (work ~ n^2 * P, all SMs),
+ * beyond it one CTA that is parallel within a permutation (bracketing prefix sums per mask epoch).
  * workspace: mmx_perm_shuffle_workspace_bytes(n, P, n_words). */
 int mmx_perm_shuffle_workspace_bytes(int n, int P, int64_t n_words, size_t* bytes);
 int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, int P, int32_t* perm, int64_t* info,
