@@ -3,11 +3,18 @@ CPU path, timed on the host cores) prints exactly ONE JSON line on stdout with t
 metric / unit / config as the GPU arm; under torchrun only rank 0 works and prints."""
 import json
 import os
+import socket
 import subprocess
 import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
 
 
 def _run(cmd, env=None):
@@ -40,7 +47,7 @@ def test_reference_arm_prints_one_json_line_on_our_config():
 def test_reference_arm_under_torchrun_only_rank0_prints():
     env = dict(os.environ, OMP_NUM_THREADS="2")
     lines = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                  "--master-addr", "127.0.0.1", "--master-port", "29577", "bench.py", "--impl", "reference",
+                  "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), "bench.py", "--impl", "reference",
                   "--gpus", "2", "--steps", "1", "--warmup", "0"], env=env)
     json_lines = [l for l in lines if l.startswith("{")]
     assert len(json_lines) == 1
