@@ -1,0 +1,145 @@
+"""numpy emulation of emit_long_kernel v2 (csrc/shuffle.cu): one CTA of T threads, every thread owns S consecutive
+words of the epoch's window (S odd), Gauss-Seidel inside a segment (the running brackets l <= a(t) <= u are updated
+word by word), Jacobi across segments (one block-wide scan of the packed (l, u) counts per round), convergence =
+every thread whose lower base is below the epoch's step count has an exact base. Checked against numpy's shuffle
+(permutations and stream position) before the kernel first ran on a GPU.
+
+    python dev/emul_emit_long2.py
+"""
+import math
+import sys
+
+import numpy as np
+
+T = 1024
+RING = 57344
+WCAP = RING - 8
+SERIAL_BELOW = 64          # steps with i < 64 are walked by one thread
+
+
+def plan_epochs(n):
+    """(i_hi, c, M, W0) per mask epoch, top down; W0 = expected words + 8 sigma + 64."""
+    out = []
+    i_hi = n - 1
+    while i_hi >= SERIAL_BELOW:
+        b = int(i_hi).bit_length()
+        M = (1 << b) - 1
+        i_lo = max(1 << (b - 1), SERIAL_BELOW)
+        i = np.arange(i_lo, i_hi + 1, dtype=np.float64)
+        p = (i + 1.0) / (M + 1.0)
+        mean = float(np.sum(1.0 / p))
+        sig = math.sqrt(float(np.sum((1.0 - p) / p ** 2)))
+        W0 = min(WCAP, int(mean + 8.0 * sig) + 64)
+        out.append((i_hi, i_hi - i_lo + 1, M, W0))
+        i_hi = i_lo - 1
+    return out, i_hi        # i_hi = first step of the serial tail (SERIAL_BELOW - 1, or n - 1 if smaller)
+
+
+def epoch(words, pos, n_words, i_hi, c, M, W0, stats):
+    W = W0
+    while True:
+        W = min(W, n_words - pos)
+        if W < c:
+            return None, -1
+        S = -(-W // T)
+        S |= 1
+        v = np.full(T * S, 1 << 40, dtype=np.int64)
+        v[:W] = words[pos:pos + W].astype(np.int64) & M
+        v = v.reshape(T, S)
+        t0 = np.arange(T, dtype=np.int64) * S
+        Lb = np.zeros(T, dtype=np.int64)
+        Ub = np.minimum(t0, W)
+        rnd = 0
+        while True:
+            l, u = Lb.copy(), Ub.copy()
+            for s in range(S):
+                a1 = (v[:, s] + u) <= i_hi
+                a2 = (v[:, s] + l) <= i_hi
+                l += a1
+                u += a2
+            pred = (Lb >= c) | (Lb == Ub) | (t0 >= W)
+            if pred.all():
+                break
+            cl, cu = l - Lb, u - Ub
+            assert (cl <= cu).all()
+            Lb = np.cumsum(cl) - cl
+            Ub = np.cumsum(cu) - cu
+            rnd += 1
+            assert rnd <= T
+        stats.append(rnd)
+        # emit with exact bases
+        out = np.full(c, -1, dtype=np.int64)
+        end = -1
+        l = Lb.copy()
+        for s in range(S):
+            acc = ((v[:, s] + l) <= i_hi) & (Lb < c)
+            w = acc & (l < c)
+            out[l[w]] = v[w, s]
+            last = w & (l == c - 1)
+            if last.any():
+                assert last.sum() == 1
+                end = int(t0[last][0]) + s + 1
+            l += acc
+        if end >= 0:
+            assert (out >= 0).all()
+            return out, end
+        if W >= WCAP or pos + W >= n_words:
+            return None, (-3 if W >= WCAP else -1)
+        W = min(WCAP, 2 * W)
+
+
+def emit_long(words, n, P):
+    n_words = len(words) & ~3
+    plan, i_tail = plan_epochs(n)
+    jout = np.zeros(P * (n - 1), dtype=np.int64)
+    pos, stats = 0, []
+    for p in range(P):
+        base = p * (n - 1)
+        for (i_hi, c, M, W0) in plan:
+            out, end = epoch(words, pos, n_words, i_hi, c, M, W0, stats)
+            if out is None:
+                return None, end, stats
+            jout[base + (n - 1 - i_hi): base + (n - 1 - i_hi) + c] = out
+            pos += end
+        i = i_tail
+        while i >= 1:                                       # serial tail (thread 0)
+            if pos >= n_words:
+                return None, -1, stats
+            mask = (1 << int(i).bit_length()) - 1
+            vv = int(words[pos]) & mask
+            pos += 1
+            if vv <= i:
+                jout[base + (n - 1 - i)] = vv
+                i -= 1
+    return jout, pos, stats
+
+
+def check(n, P, seed=7):
+    ref = np.random.RandomState(seed)
+    raw = np.random.RandomState(seed)
+    words = raw._bit_generator.random_raw(int(P * n * 2.0) + 100000).astype(np.uint32)
+    jout, pos, st = emit_long(words, n, P)
+    assert jout is not None, pos
+    x, xr = np.arange(n), np.arange(n)
+    ok = True
+    for p in range(P):
+        ref.shuffle(xr)
+        js = jout[p * (n - 1):(p + 1) * (n - 1)]
+        for k, i in enumerate(range(n - 1, 0, -1)):
+            j = js[k]
+            x[i], x[j] = x[j], x[i]
+        ok = ok and np.array_equal(x, xr)
+    chk = np.random.RandomState(seed)
+    chk._bit_generator.random_raw(pos)
+    same_state = chk.randint(0, 1 << 30) == ref.randint(0, 1 << 30)
+    print(n, P, ok, same_state, "rounds max", max(st) if st else 0, "mean %.2f" % (np.mean(st) if st else 0),
+          "sum/perm", sum(st) / P)
+    assert ok and same_state
+
+
+if __name__ == "__main__":
+    for n, P in ((50000, 3), (20000, 4), (16385, 3), (65536, 2), (40000, 2), (100, 50), (2, 5), (3, 5), (64, 9), (65, 9),
+                 (1500, 20)):
+        check(n, P)
+    words = np.random.RandomState(1)._bit_generator.random_raw(30000).astype(np.uint32)
+    print("short stream ->", emit_long(words, 20000, 2)[1])

@@ -32,7 +32,7 @@ CSV_COLUMNS = (["Model"] + [f"{k}_{s}" for k in METRIC_KEYS for s in ("mean", "l
                + ["Time", "QPS", "Encoding_Time", "Img_per_sec", "_failure_analysis"])  # main.py:643-665
 N_BOOTSTRAP = 10000       # main.py:265
 CHUNK = 10                # main.py:453
-DEVICE_SHUFFLE_MAX_N = 16384  # permutation tests on longer arrays replay np.random.shuffle on the host (K6s cost ~ n^2)
+DEVICE_SHUFFLE_MAX_N = 65536  # longest array whose shuffles are replayed on the device (K6s: table scheme up to 16 384, one-CTA bracket scheme beyond)
 DEVICE_RNG = True         # draw the reference's numpy MT19937 stream on the GPU (K6); False = numpy draws on the host
 
 

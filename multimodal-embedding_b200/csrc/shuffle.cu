@@ -23,6 +23,9 @@
 //               a scan over the block composites, then each block replayed from its prefix): [P, n] index rows,
 //               which is what K5 (mmx_perm_stats) consumes.
 // Bit-exact against numpy by construction; tests/test_gpu_parity.py compares the index rows and the generator state.
+#include <algorithm>
+#include <cmath>
+
 #include "../../include/mmx.h"
 #include "mmx_host.cuh"
 
@@ -36,32 +39,41 @@ constexpr int PB = 64;         // permutations per composition block
 constexpr int MAX_N = 16384;   // B/C/D: work grows with n * |W| (~n^2 P); longer arrays take the LONG emit below
 constexpr int MAX_N_LONG = 65536;   // LONG emit: masked values fit uint16
 constexpr int LT = 1024;            // threads of the LONG emit CTA
-constexpr int LW_MAX = 65536;       // words of one mask epoch's window (uint16 values + one flag byte each: 192 KB)
 
 struct Plan {
     long long n_chunks, steps;
-    int n_blocks;
-    bool long_n;
-    size_t off_tab, off_m, off_s, off_j, off_arr, off_pi, off_c, off_d, off_g, total;
+    int n_blocks, pb;
+    bool long_n, lists_in_smem, rows_in_smem;
+    int apply_grid;
+    size_t off_tab, off_m, off_s, off_j, off_arr, off_pi, off_c, off_d, off_g, off_l, total;
 };
+
+constexpr size_t SMEM_MAX = 227 * 1024;
 
 static Plan make_plan(int n, int P, long long n_words) {
     Plan pl{};
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     pl.n_chunks = (n_words + L - 1) / L;
     pl.steps = (long long)P * (n - 1);
-    pl.n_blocks = (P + PB - 1) / PB;
     pl.long_n = n > MAX_N;
+    // long arrays: one wave of composition CTAs covers all permutations
+    pl.pb = pl.long_n ? std::max(8, (P + sm_count() - 1) / sm_count()) : PB;
+    pl.n_blocks = (P + pl.pb - 1) / pl.pb;
+    const size_t nw = (size_t)(n + 2) / 2;
+    pl.lists_in_smem = (((nw + 3) & ~size_t(3)) * 4 + (size_t)n * 2) <= SMEM_MAX - 1024;
+    pl.rows_in_smem = (size_t)((n + 7) & ~7) * 4 <= SMEM_MAX - 1024;
+    pl.apply_grid = std::min(P, sm_count());
     size_t o = 256;
     pl.off_tab = o; o += up(pl.long_n ? 0 : (size_t)pl.n_chunks * (n - 1) * 2);   // uint16 accepts per (chunk, start state)
     pl.off_m = o;   o += up((size_t)(pl.n_chunks + 1) * 4);       // start state of every chunk
     pl.off_s = o;   o += up((size_t)(pl.n_chunks + 1) * 8);       // global step offset of every chunk
     pl.off_j = o;   o += up((size_t)pl.steps * 4);                // j of every step
-    pl.off_arr = o; o += up((size_t)n * P * 4);                   // [i][P] working arrays of stage E
+    pl.off_arr = o; o += up(pl.long_n ? 0 : (size_t)n * P * 4);   // [i][P] working arrays of stage E
     pl.off_pi = o;  o += up((size_t)n * P * 4);                   // [P][n] pi_p
     pl.off_c = o;   o += up((size_t)pl.n_blocks * n * 4);         // block composites
     pl.off_d = o;   o += up((size_t)(pl.n_blocks + 1) * n * 4);   // prefixes of the block composites
-    pl.off_g = o;   o += up(pl.long_n ? (size_t)(pl.n_blocks + 1) * 2 * n * 4 : 0);   // LONG: composition buffers in L2
+    pl.off_g = o;   o += up(pl.long_n && !pl.rows_in_smem ? (size_t)(pl.n_blocks + 1) * 2 * n * 4 : 0);  // rows in L2
+    pl.off_l = o;   o += up(pl.long_n && !pl.lists_in_smem ? (size_t)pl.apply_grid * n * 2 : 0);        // step lists in L2
     pl.total = o;
     return pl;
 }
@@ -227,164 +239,381 @@ emit_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, long 
 }
 
 // D-long: the accepted j values of P cumulative shuffles of an array too long for the table scheme (n > MAX_N), by ONE
-// CTA that is parallel WITHIN a permutation (prototype and proof of exactness against numpy: dev/proto_long_shuffle.py).
-// Inside a mask epoch (all steps i with the same mask M, i from i_hi down to i_lo) the k-th accepted word serves step
-// i_hi - k, so word t is accepted iff  v_t <= i_hi - a(t),  v_t = word_t & M,  a(t) = accepts before t. a(t) is the
-// only serial quantity; it is bracketed, L(t) <= a(t) <= U(t), and the brackets are tightened round by round:
-//     surely accepted  v_t <= i_hi - U(t)        surely rejected  v_t > i_hi - L(t)
-//     L'(t) = surely accepted words before t     U'(t) = words before t that are not surely rejected
-// — two block-wide prefix sums per round, every round exact, 4-8 rounds until L = U up to the epoch's last accept.
-// Every thread owns a contiguous segment of the epoch's window (values and one flag byte per word in shared memory).
-struct LongScan {
-    int baseA, baseU, totA, totU;
+// CTA that is parallel WITHIN a permutation (numpy emulation and proof of exactness: dev/emul_emit_long2.py).
+// Inside a mask epoch (all steps i with the same mask M, i from i_hi down to i_lo; c = i_hi - i_lo + 1 steps) the k-th
+// accepted word serves step i_hi - k, so word t is accepted iff  v_t + a(t) <= i_hi,  v_t = word_t & M,  a(t) = accepts
+// before t. a(t) is the only serial quantity. Every thread owns S consecutive words of the epoch's window and keeps a
+// bracket l <= a(t) <= u along them, updated word by word (Gauss-Seidel inside the segment):
+//     l += [v + u <= i_hi]   (surely accepted)        u += [v + l <= i_hi]   (not surely rejected)
+// starting from the bracket (Lb, Ub) of the segment's first word; one block-wide scan of the packed (l - Lb, u - Ub)
+// counts per round gives the next round's bases (Jacobi across segments). Thread 0's base is exact (0, 0), an exact
+// base makes the walk the serial simulation itself, and the brackets contract like tau^r / r! (tau = window / mask),
+// so every thread below the epoch's end is exact after ~5 rounds (one barrier each); then one more walk emits.
+// The raw words live in a shared-memory ring that cp.async refills a whole epoch ahead, the last 63 steps of a
+// permutation (masks below 64: a handful of words each) are walked by one thread.
+constexpr int RING = 57344;             // words of the ring (224 KB)
+constexpr int WCAP = RING - 8;          // longest window of one epoch
+constexpr int SERIAL_BELOW = 64;        // steps with i < 64 are walked by thread 0
+constexpr int TAIL_W = 4096;            // words the serial tail may look at
+constexpr int MAX_EPOCHS = 20;
+
+struct LongEpoch {
+    int i_hi, c, W0;
+    uint32_t M;
 };
-__device__ __forceinline__ LongScan long_block_scan(int a, int u, int* wA, int* wU, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
-    int ia = a, iu = u;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int ta = __shfl_up_sync(0xffffffffu, ia, o), tu = __shfl_up_sync(0xffffffffu, iu, o);
-        if (lane >= o) {
-            ia += ta;
-            iu += tu;
+struct LongPlan {
+    int n_epochs, i_tail;
+    LongEpoch e[MAX_EPOCHS];
+};
+
+static LongPlan make_long_plan(int n) {
+    LongPlan pl{};
+    int i_hi = n - 1;
+    while (i_hi >= SERIAL_BELOW && pl.n_epochs < MAX_EPOCHS) {
+        int b = 0;
+        while ((1ll << b) <= i_hi) ++b;                  // bit length of i_hi
+        const uint32_t M = (uint32_t)((1ull << b) - 1);
+        const int i_lo = std::max(1 << (b - 1), SERIAL_BELOW);
+        double mean = 0.0, var = 0.0;
+        for (int i = i_lo; i <= i_hi; ++i) {
+            const double p = (i + 1.0) / ((double)M + 1.0);
+            mean += 1.0 / p;
+            var += (1.0 - p) / (p * p);
         }
+        LongEpoch& e = pl.e[pl.n_epochs++];
+        e.i_hi = i_hi;
+        e.c = i_hi - i_lo + 1;
+        e.M = M;
+        e.W0 = (int)std::min<double>(WCAP, mean + 8.0 * std::sqrt(var) + 64.0);
+        i_hi = i_lo - 1;
     }
-    __syncthreads();  // the previous use of wA / wU is over
-    if (lane == 31) {
-        wA[warp] = ia;
-        wU[warp] = iu;
-    }
-    __syncthreads();
-    int pa = 0, pu = 0, sa = 0, su = 0;
-#pragma unroll
-    for (int w = 0; w < LT / 32; ++w) {
-        const int ca = wA[w], cu = wU[w];
-        if (w < warp) {
-            pa += ca;
-            pu += cu;
-        }
-        sa += ca;
-        su += cu;
-    }
-    LongScan r;
-    r.baseA = pa + ia - a;
-    r.baseU = pu + iu - u;
-    r.totA = sa;
-    r.totU = su;
-    return r;
+    pl.i_tail = i_hi;
+    return pl;
 }
 
-__global__ void __launch_bounds__(LT)
-emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, int P, long long* __restrict__ info,
-                 int32_t* __restrict__ jout) {
-    extern __shared__ uint8_t lsm[];
-    uint16_t* sv = reinterpret_cast<uint16_t*>(lsm);  // [LW_MAX] masked values of the window
-    uint8_t* sf = lsm + (size_t)LW_MAX * 2;           // [LW_MAX] bit 0 = surely accepted, bit 1 = surely rejected
-    __shared__ int wA[LT / 32], wU[LT / 32];
-    __shared__ int s_done_at, s_conv;
-    const int tid = threadIdx.x;
-    long long pos = 0, step_base = 0;
-    for (int p = 0; p < P; ++p, step_base += n - 1) {
-        int i_hi = n - 1;
-        while (i_hi >= 1) {
-            const int b = 32 - __clz(i_hi);
-            const uint32_t M = (b >= 32) ? 0xffffffffu : ((1u << b) - 1u);
-            const int i_lo = max(1 << (b - 1), 1);
-            const int c = i_hi - i_lo + 1;
-            int W = min(LW_MAX, (int)(1.40f * (float)c) + 1024);
-            bool epoch_done = false;
-            while (!epoch_done) {
-                if (pos + W > n_words) W = (int)(n_words - pos);
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(LT, 1)
+emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, int P,
+                 const __grid_constant__ LongPlan plan, long long* __restrict__ info, int32_t* __restrict__ jout) {
+    extern __shared__ uint32_t ring[];  // [RING] word g of the stream sits at ring[g % RING]
+    __shared__ uint32_t wtot[2][LT / 32];
+    __shared__ int s_end;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    n_words &= ~3ll;                    // 16-byte copies only
+    long long pos = 0;                  // first word not consumed yet
+    long long loaded = 0;               // words [.., loaded) are in the ring or on their way
+    int pos_mod = 0;                    // pos % RING
+    int err = 0;
+
+    // refill the ring up to pos + RING (the slots of consumed words), wait until [pos, pos + W) has landed
+    auto stage = [&](int W) {
+        __syncthreads();  // everybody is done reading the consumed words (and has seen s_end)
+        if (tid == 0) s_end = -1;
+        const long long until_prev = loaded;
+        const long long until = min(n_words, (pos + RING) & ~3ll);
+        if (until > loaded) {
+            long long g = loaded + 4ll * tid;
+            int r = (int)(g % RING);
+            for (; g < until; g += 4ll * LT) {
+                cp_async16(ring + r, words + g);
+                r += 4 * LT;
+                if (r >= RING) r -= RING;
+            }
+            loaded = until;
+        }
+        cp_async_commit();
+        if (pos + W <= until_prev) cp_async_wait<1>();  // this epoch's refill stays in flight
+        else cp_async_wait<0>();
+        __syncthreads();
+    };
+
+    for (int p = 0; p < P && !err; ++p) {
+        int32_t* const jp = jout + (long long)p * (n - 1);
+        for (int e = 0; e < plan.n_epochs && !err; ++e) {
+            const int i_hi = plan.e[e].i_hi, c = plan.e[e].c;
+            const uint32_t M = plan.e[e].M;
+            int W = plan.e[e].W0;
+            for (;;) {
+                W = (int)min((long long)W, n_words - pos);
                 if (W < c) {  // the stream is too short: the caller retries with more words
-                    if (tid == 0) {
-                        info[0] = -1;
-                        info[1] = -1;
-                    }
-                    return;
+                    err = -1;
+                    break;
                 }
-                __syncthreads();  // everybody is done with the previous window
-                for (int t = tid; t < W; t += LT) {
-                    const uint32_t v = words[pos + t] & M;
-                    sv[t] = (uint16_t)v;
-                    sf[t] = (v <= (uint32_t)i_hi) ? 0 : 2;  // a(t) >= 0: a word above i_hi is never accepted
+                stage(W);
+                int S = (W + LT - 1) / LT;
+                S |= 1;  // odd: the threads of a warp walk distinct banks
+                const int t0 = min(W, tid * S), len = min(W, t0 + S) - t0;
+                int r0 = pos_mod + t0;
+                if (r0 >= RING) r0 -= RING;
+                const int len1 = min(len, RING - r0);  // words before the ring wraps
+                int Lb = 0, Ub = t0;
+                int walked = -1, wl = 0;  // exact base of the last single-chain walk and its count
+                for (int rnd = 0;; ++rnd) {
+                    uint32_t pk;
+                    if (Lb == Ub) {
+                        if (walked != Lb) {  // exact base: the walk is the serial simulation of the segment
+                            int l = Lb;
+                            for (int k = 0; k < len1; ++k) l += ((int)(ring[r0 + k] & M) + l <= i_hi) ? 1 : 0;
+                            for (int k = len1; k < len; ++k) l += ((int)(ring[r0 + k - RING] & M) + l <= i_hi) ? 1 : 0;
+                            walked = Lb;
+                            wl = l - Lb;
+                        }
+                        pk = (uint32_t)wl | ((uint32_t)wl << 16);
+                    } else {
+                        int l = Lb, u = Ub;
+                        for (int k = 0; k < len1; ++k) {
+                            const int v = (int)(ring[r0 + k] & M);
+                            const int a1 = (v + u <= i_hi) ? 1 : 0, a2 = (v + l <= i_hi) ? 1 : 0;
+                            l += a1;
+                            u += a2;
+                        }
+                        for (int k = len1; k < len; ++k) {
+                            const int v = (int)(ring[r0 + k - RING] & M);
+                            const int a1 = (v + u <= i_hi) ? 1 : 0, a2 = (v + l <= i_hi) ? 1 : 0;
+                            l += a1;
+                            u += a2;
+                        }
+                        pk = (uint32_t)(l - Lb) | ((uint32_t)(u - Ub) << 16);
+                    }
+                    uint32_t incl = pk;  // inclusive scan of both counts at once (each stays below 2^16)
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    if (lane == 31) wtot[rnd & 1][warp] = incl;
+                    const int settled = (Lb >= c) || (Lb == Ub) || (len == 0);
+                    if (__syncthreads_and(settled)) break;
+                    uint32_t ws = wtot[rnd & 1][lane];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+                        if (lane >= o) ws += t;
+                    }
+                    uint32_t base = __shfl_sync(0xffffffffu, ws, (warp + 31) & 31);
+                    if (warp == 0) base = 0;
+                    base += incl - pk;
+                    Lb = (int)(base & 0xffffu);
+                    Ub = (int)(base >> 16);
+                }
+                // ---- emit: the k-th accepted word of the epoch is the j of step i_hi - k
+                if (Lb < c) {
+                    int32_t* out = jp + (n - 1 - i_hi);
+                    int l = Lb;
+                    for (int k = 0; k < len && l < c; ++k) {
+                        const int r = r0 + k;
+                        const int v = (int)(ring[r >= RING ? r - RING : r] & M);
+                        if (v + l <= i_hi) {
+                            out[l] = v;
+                            if (++l == c) s_end = t0 + k + 1;
+                        }
+                    }
                 }
                 __syncthreads();
-                const int S = (W + LT - 1) / LT;
-                const int t0 = min(W, tid * S), t1 = min(W, t0 + S);
-                int prevA = -1, prevU = -1;
-                for (int round = 0;; ++round) {
-                    // ---- counts of the current flags, their block-wide exclusive prefixes
-                    int a = 0, u = 0;
-                    for (int t = t0; t < t1; ++t) {
-                        const int f = sf[t];
-                        a += f & 1;
-                        u += (f >> 1) ^ 1;
-                    }
-                    const LongScan sc = long_block_scan(a, u, wA, wU, tid);
-                    if (tid == 0) s_done_at = -1;
-                    __syncthreads();
-                    // ---- the thread whose segment holds the c-th sure accept: is everything before it settled?
-                    if (sc.baseA < c && sc.baseA + a >= c) {
-                        int ra = sc.baseA, ru = sc.baseU;
-                        for (int t = t0; t < t1; ++t) {
-                            const int f = sf[t];
-                            ra += f & 1;
-                            ru += (f >> 1) ^ 1;
-                            if (ra == c) {
-                                s_done_at = t;
-                                s_conv = (ru == c) ? 1 : 0;  // U = L up to and including the last accept
-                                break;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                    const int done_at = s_done_at;
-                    if (done_at >= 0 && s_conv) {
-                        // ---- emit: the k-th accepted word of the epoch is the j of step i_hi - k
-                        int ra = sc.baseA;
-                        int32_t* out = jout + step_base + (n - 1 - i_hi);
-                        for (int t = t0; t < t1 && ra < c; ++t)
-                            if (sf[t] & 1) out[ra++] = (int32_t)sv[t];
-                        pos += done_at + 1;
-                        epoch_done = true;
-                        break;
-                    }
-                    if (sc.totA == prevA && sc.totU == prevU) {
-                        // no flag changed in the last round and the c-th accept is not settled: the window is too short
-                        if (W >= LW_MAX || pos + W >= n_words) {
-                            if (tid == 0) {
-                                info[0] = -1;
-                                info[1] = (W >= LW_MAX) ? -3 : -1;
-                            }
-                            return;
-                        }
-                        W = min(LW_MAX, 2 * W);
-                        break;  // restage a longer window of the same epoch
-                    }
-                    prevA = sc.totA;
-                    prevU = sc.totU;
-                    // ---- tighten: new flags from the brackets L(t) = ra, U(t) = ru of the OLD flags
-                    {
-                        int ra = sc.baseA, ru = sc.baseU;
-                        for (int t = t0; t < t1; ++t) {
-                            const int f = sf[t];
-                            const int v = sv[t];
-                            const int nf = (v <= i_hi - ru ? 1 : 0) | (v > i_hi - ra ? 2 : 0);
-                            ra += f & 1;
-                            ru += (f >> 1) ^ 1;
-                            sf[t] = (uint8_t)nf;
-                        }
-                    }
-                    // each thread rewrote only its own segment; the next round's scan synchronises before any
-                    // cross-thread read
+                const int end = s_end;
+                if (end >= 0) {
+                    pos += end;
+                    pos_mod += end;
+                    if (pos_mod >= RING) pos_mod -= RING;
+                    break;
                 }
+                // the c-th accept is not inside the window: stage a longer one
+                if (W >= WCAP || pos + W >= n_words) {
+                    err = (W >= WCAP) ? -3 : -1;
+                    break;
+                }
+                W = min(WCAP, 2 * W);
             }
-            i_hi = i_lo - 1;
+        }
+        if (err) break;
+        // ---- serial tail: the steps i < SERIAL_BELOW
+        if (plan.i_tail >= 1) {
+            const int W = (int)min((long long)TAIL_W, n_words - pos);
+            stage(W);
+            if (tid == 0) {
+                int i = plan.i_tail, k = 0;
+                int32_t* out = jp + (n - 1);
+                for (; k < W && i >= 1; ++k) {
+                    const int r = pos_mod + k;
+                    const uint32_t mask = 0xffffffffu >> __clz(i);
+                    const int v = (int)(ring[r >= RING ? r - RING : r] & mask);
+                    if (v <= i) {
+                        out[-i] = v;
+                        --i;
+                    }
+                }
+                s_end = (i == 0) ? k : -1;
+            }
+            __syncthreads();
+            const int end = s_end;
+            if (end < 0) {
+                err = (W >= TAIL_W) ? -3 : -1;
+                break;
+            }
+            pos += end;
+            pos_mod += end;
+            if (pos_mod >= RING) pos_mod -= RING;
         }
     }
     if (tid == 0) {
-        info[0] = 0;
-        info[1] = pos;  // exactly this many words were consumed
+        info[0] = err ? -1 : 0;
+        info[1] = err ? err : pos;  // exactly this many words were consumed
+    }
+}
+
+// E-long: permutation p (the result of its n-1 swaps on an identity array) without replaying the swaps one by one.
+// Step i (i = n-1 .. 1) exchanges positions i and j_i <= i, after which position i is final. The value a position q
+// holds just before step i was put there by the most recent earlier step that targeted q — the smallest i' > i with
+// j_i' = q — and is whatever position i' held just before step i'; without such a step it is q itself. So
+//     pi[i] = root(first(j_i, i)),  first(q, i) = min{ i' > i : j_i' = q },  root(x) = follow first(x, x) to the end,
+// a pointer chase of expected depth O(log n) over the steps grouped by target (CSR built with packed 16-bit shared
+// atomics). One CTA per permutation; every position is resolved independently.
+constexpr int AT = 1024;
+__global__ void __launch_bounds__(AT, 1)
+apply_long_kernel(const int32_t* __restrict__ jout, int n, int P, const long long* __restrict__ info,
+                  int32_t* __restrict__ pi, uint16_t* __restrict__ glist) {
+    extern __shared__ uint32_t asm32[];
+    // cur[q] (uint16, packed two per word): while filling, the cursor of target q; afterwards the END of q's list
+    uint32_t* cur = asm32;                                    // [(n + 2) / 2] words
+    __shared__ uint32_t wsum[AT / 32];
+    if (info[1] < 0) return;  // too few words: jout is incomplete, the caller retries
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nw = (n + 2) / 2;
+    uint16_t* lst = glist != nullptr ? glist + (size_t)blockIdx.x * n
+                                     : reinterpret_cast<uint16_t*>(asm32 + ((nw + 3) & ~3));
+    const uint16_t* cur16 = reinterpret_cast<const uint16_t*>(cur);
+    for (int p = blockIdx.x; p < P; p += gridDim.x) {
+        const int32_t* jp = jout + (long long)p * (n - 1);  // jp[n - 1 - i] = j_i
+        __syncthreads();
+        for (int w = tid; w < nw; w += AT) cur[w] = 0;
+        __syncthreads();
+        for (int i = 1 + tid; i < n; i += AT) {
+            const int q = jp[n - 1 - i];
+            atomicAdd(&cur[q >> 1], 1u << ((q & 1) * 16));
+        }
+        __syncthreads();
+        // exclusive scan of the n 16-bit counts, in place (every thread owns a contiguous run of words)
+        {
+            const int per = (nw + AT - 1) / AT;
+            const int w0 = min(nw, tid * per), w1 = min(nw, w0 + per);
+            uint32_t s = 0;
+            for (int w = w0; w < w1; ++w) {
+                const uint32_t x = cur[w];
+                s += (x & 0xffffu) + (x >> 16);
+            }
+            uint32_t incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) wsum[warp] = incl;
+            __syncthreads();
+            uint32_t ws = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            uint32_t run = __shfl_sync(0xffffffffu, ws, (warp + 31) & 31);
+            if (warp == 0) run = 0;
+            run += incl - s;
+            for (int w = w0; w < w1; ++w) {
+                const uint32_t x = cur[w];
+                const uint32_t lo = run, hi = run + (x & 0xffffu);
+                run = hi + (x >> 16);
+                cur[w] = (lo & 0xffffu) | (hi << 16);  // offsets stay below n - 1 <= 65535
+            }
+        }
+        __syncthreads();
+        for (int i = 1 + tid; i < n; i += AT) {
+            const int q = jp[n - 1 - i];
+            const uint32_t old = atomicAdd(&cur[q >> 1], 1u << ((q & 1) * 16));
+            lst[(old >> ((q & 1) * 16)) & 0xffffu] = (uint16_t)i;
+        }
+        __syncthreads();
+        // list of target q = lst[begin(q) .. cur16[q]), begin(q) = cur16[q - 1] (0 for q = 0)
+        int32_t* row = pi + (long long)p * n;
+        for (int x = tid; x < n; x += AT) {
+            int q = x >= 1 ? jp[n - 1 - x] : 0;
+            int above = x;  // look for the smallest step > above that targeted q
+            for (;;) {
+                const int b = q > 0 ? cur16[q - 1] : 0, e = cur16[q];
+                int best = 0x7fffffff;
+                for (int k = b; k < e; ++k) {
+                    const int s = lst[k];
+                    if (s > above && s < best) best = s;
+                }
+                if (best == 0x7fffffff) break;
+                q = best;
+                above = best;
+            }
+            row[x] = q;
+        }
+    }
+}
+
+// F-long: the same three composition phases as below with the two working rows in shared memory as uint16
+// (n <= 56 000: 2 x 2 n bytes), PB_long permutations per block so that one wave of CTAs covers all of them.
+__global__ void __launch_bounds__(1024, 1)
+compose_block16_kernel(const int32_t* __restrict__ pi, int n, int P, int pb, const int32_t* __restrict__ start,
+                       int32_t* __restrict__ comp_out, int32_t* __restrict__ rows_out) {
+    extern __shared__ uint16_t sm16[];
+    const int b = blockIdx.x;
+    const int np = (n + 7) & ~7;
+    uint16_t* cur = sm16;
+    uint16_t* nxt = sm16 + np;
+    for (int k = threadIdx.x; k < n; k += blockDim.x)
+        cur[k] = (uint16_t)(start != nullptr ? start[(long long)b * n + k] : k);
+    __syncthreads();
+    const int p_end = min(P, (b + 1) * pb);
+    for (int p = b * pb; p < p_end; ++p) {
+        const int32_t* row = pi + (long long)p * n;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const uint16_t x = cur[row[k]];
+            nxt[k] = x;
+            if (rows_out != nullptr) rows_out[(long long)p * n + k] = x;
+        }
+        __syncthreads();
+        uint16_t* t = cur;
+        cur = nxt;
+        nxt = t;
+    }
+    if (comp_out != nullptr)
+        for (int k = threadIdx.x; k < n; k += blockDim.x) comp_out[(long long)b * n + k] = cur[k];
+}
+
+__global__ void __launch_bounds__(1024, 1)
+compose_scan16_kernel(const int32_t* __restrict__ comp, int n, int n_blocks, int32_t* __restrict__ prefix) {
+    extern __shared__ uint16_t sm16[];
+    const int np = (n + 7) & ~7;
+    uint16_t* cur = sm16;
+    uint16_t* nxt = sm16 + np;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        cur[k] = (uint16_t)k;
+        prefix[k] = k;
+    }
+    __syncthreads();
+    for (int b = 0; b < n_blocks; ++b) {
+        const int32_t* c = comp + (long long)b * n;
+        for (int k = threadIdx.x; k < n; k += blockDim.x) {
+            const uint16_t x = cur[c[k]];
+            nxt[k] = x;
+            prefix[(long long)(b + 1) * n + k] = x;
+        }
+        __syncthreads();
+        uint16_t* t = cur;
+        cur = nxt;
+        nxt = t;
     }
 }
 
@@ -420,7 +649,7 @@ transpose_kernel(const int32_t* __restrict__ src, int n, int P, int32_t* __restr
 // F1 / F3: CTA b composes the permutations of its block in order, starting from `start` (nullptr = identity);
 // write_rows = 1 stores every intermediate row (the result), 0 stores only the block composite.
 __global__ void __launch_bounds__(512)
-compose_block_kernel(const int32_t* __restrict__ pi, int n, int P, const int32_t* __restrict__ start,
+compose_block_kernel(const int32_t* __restrict__ pi, int n, int P, int pb, const int32_t* __restrict__ start,
                      int32_t* __restrict__ comp_out, int32_t* __restrict__ rows_out, int32_t* gbuf) {
     extern __shared__ int32_t sm[];
     const int b = blockIdx.x;
@@ -429,8 +658,8 @@ compose_block_kernel(const int32_t* __restrict__ pi, int n, int P, const int32_t
     int32_t* nxt = cur + n;
     for (int k = threadIdx.x; k < n; k += blockDim.x) cur[k] = start != nullptr ? start[(long long)b * n + k] : k;
     __syncthreads();
-    const int p_end = min(P, (b + 1) * PB);
-    for (int p = b * PB; p < p_end; ++p) {
+    const int p_end = min(P, (b + 1) * pb);
+    for (int p = b * pb; p < p_end; ++p) {
         const int32_t* row = pi + (long long)p * n;
         for (int k = threadIdx.x; k < n; k += blockDim.x) {
             const int32_t x = cur[row[k]];
@@ -504,15 +733,44 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
     int32_t* gbuf = pl.long_n ? reinterpret_cast<int32_t*>(ws + pl.off_g - 256) : nullptr;
     const int n1 = n - 1;
     if (pl.long_n) {
-        // n > MAX_N: one CTA, parallel within a permutation (bracketing prefix sums per mask epoch)
-        const size_t smem_long = (size_t)LW_MAX * 3;
+        // n > MAX_N: the emit is one CTA that is parallel within a permutation (bracketing prefix sums per mask epoch),
+        // the swaps are resolved per position by a pointer chase, the composition keeps its rows in shared memory
+        const LongPlan lp = make_long_plan(n);
+        const size_t smem_long = (size_t)RING * 4;
         static const char long_attr_tag = 0;
-        if (first_use_on_device(&long_attr_tag))
+        if (first_use_on_device(&long_attr_tag)) {
             MMX_CHECK_CUDA(cudaFuncSetAttribute(emit_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)smem_long));
-        emit_long_kernel<<<1, LT, smem_long, stream>>>(words, n_words, n, P, reinterpret_cast<long long*>(info), jout);
+            MMX_CHECK_CUDA(cudaFuncSetAttribute(apply_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(SMEM_MAX - 1024)));
+            MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_block16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(SMEM_MAX - 1024)));
+            MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_scan16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(SMEM_MAX - 1024)));
+        }
+        emit_long_kernel<<<1, LT, smem_long, stream>>>(words, n_words, n, P, lp, reinterpret_cast<long long*>(info), jout);
         MMX_CHECK_CUDA(cudaGetLastError());
-    } else {
+        const size_t nw = (size_t)(n + 2) / 2;
+        const size_t smem_apply = ((nw + 3) & ~size_t(3)) * 4 + (pl.lists_in_smem ? (size_t)n * 2 : 0);
+        uint16_t* glist = pl.lists_in_smem ? nullptr : reinterpret_cast<uint16_t*>(ws + pl.off_l - 256);
+        apply_long_kernel<<<pl.apply_grid, AT, smem_apply, stream>>>(jout, n, P, reinterpret_cast<const long long*>(info),
+                                                                     pi, glist);
+        MMX_CHECK_CUDA(cudaGetLastError());
+        if (pl.rows_in_smem) {
+            const size_t smem16 = (size_t)((n + 7) & ~7) * 4;
+            compose_block16_kernel<<<pl.n_blocks, 1024, smem16, stream>>>(pi, n, P, pl.pb, nullptr, comp, nullptr);
+            compose_scan16_kernel<<<1, 1024, smem16, stream>>>(comp, n, pl.n_blocks, prefix);
+            compose_block16_kernel<<<pl.n_blocks, 1024, smem16, stream>>>(pi, n, P, pl.pb, prefix, nullptr, perm);
+        } else {
+            int32_t* gscan = gbuf + (size_t)pl.n_blocks * 2 * n;
+            compose_block_kernel<<<pl.n_blocks, 512, 0, stream>>>(pi, n, P, pl.pb, nullptr, comp, nullptr, gbuf);
+            compose_scan_kernel<<<1, 512, 0, stream>>>(comp, n, pl.n_blocks, prefix, gscan);
+            compose_block_kernel<<<pl.n_blocks, 512, 0, stream>>>(pi, n, P, pl.pb, prefix, nullptr, perm, gbuf);
+        }
+        MMX_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
+    {
         const size_t smem_tab = (size_t)(RW + CT) * 4 + 3 * (size_t)((n1 + 1) & ~1) * 2;
         static const char tab_attr_tag = 0;
         if (first_use_on_device(&tab_attr_tag)) {
@@ -533,16 +791,15 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
     apply_kernel<<<(P + 127) / 128, 128, 0, stream>>>(jout, n, P, reinterpret_cast<const long long*>(info), arr);
     dim3 gt((unsigned)((P + 31) / 32), (unsigned)((n + 31) / 32));
     transpose_kernel<<<gt, 256, 0, stream>>>(arr, n, P, pi);
-    const size_t smem = pl.long_n ? 0 : (size_t)n * 8;
+    const size_t smem = (size_t)n * 8;
     static const char attr_set_tag = 0;
     if (first_use_on_device(&attr_set_tag)) {
         MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_N * 8));
         MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_N * 8));
     }
-    int32_t* gscan = pl.long_n ? gbuf + (size_t)pl.n_blocks * 2 * n : nullptr;
-    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, nullptr, comp, nullptr, gbuf);
-    compose_scan_kernel<<<1, 512, smem, stream>>>(comp, n, pl.n_blocks, prefix, gscan);
-    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, prefix, nullptr, perm, gbuf);
+    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, pl.pb, nullptr, comp, nullptr, nullptr);
+    compose_scan_kernel<<<1, 512, smem, stream>>>(comp, n, pl.n_blocks, prefix, nullptr);
+    compose_block_kernel<<<pl.n_blocks, 512, smem, stream>>>(pi, n, P, pl.pb, prefix, nullptr, perm, nullptr);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -157,104 +157,189 @@ boot_counts_kernel(const int32_t* __restrict__ list_t, int L, const int32_t* __r
 }
 
 // ------------------------------------------------------------------------------------------- numpy pairwise sums
-// The recursion tree of numpy's pairwise sum for a given n, flattened on the host: leaves (<= 128 elements, eight
-// interleaved accumulators) in left-to-right order, each followed by the number of stack merges it completes.
-constexpr int MAX_LEAVES = 320;
-struct Program {
-    int n_leaves;
-    uint16_t size[MAX_LEAVES];
-    uint8_t merges[MAX_LEAVES];
-};
+// numpy's add.reduce over a contiguous fp64 vector is a pairwise sum (numpy/core/src/umath/loops_utils.h.src):
+//   n < 8: sequential from 0.0;  n <= 128: eight interleaved accumulators r[i % 8], then ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)),
+//   then the n % 8 leftovers sequentially;  n > 128: split at n2 = (n / 2) & ~7 and add the two halves.
+// The recursion tree for a given n is flattened into its leaves in left-to-right order, each with the number of
+// stack merges it completes; every CTA builds that list once in shared memory (one thread, an explicit stack — a few
+// hundred leaves at most), so there is no limit on n. All leaves but the last have a multiple of 8 elements.
+//
+// gather_mean_kernel: one thread per resample row, 128 rows per CTA. The index rows are streamed through a 4-stage
+// cp.async ring of [128 rows x 32 columns] tiles (16-byte copies, 8 consecutive threads fetch 128 contiguous bytes
+// of one row; the 16-byte chunks of a row are XOR-swizzled so that every thread reads its own row with conflict-free
+// LDS.128), so the global traffic is fully coalesced although every thread walks its own row in numpy's order.
+constexpr int GR = 128;      // rows per CTA = threads
+constexpr int GC = 32;       // columns per tile
+constexpr int GST = 4;       // tiles in flight
+constexpr int DATA_SMEM_MAX = 96 * 1024;
 
-static void gen_program(long long n, std::vector<std::pair<int, int>>& out) {
-    if (n <= 128) {
-        out.push_back({(int)n, 0});
-        return;
-    }
-    long long n2 = n / 2;
-    n2 -= n2 % 8;
-    gen_program(n2, out);
-    gen_program(n - n2, out);
-    out.back().second += 1;
-}
-static int make_program(long long n, Program* p) {
-    std::vector<std::pair<int, int>> v;
-    gen_program(n, v);
-    MMX_REQUIRE((int)v.size() <= MAX_LEAVES, "vector too long for the pairwise-sum program (n=%lld)", n);
-    p->n_leaves = (int)v.size();
-    for (size_t i = 0; i < v.size(); ++i) {
-        p->size[i] = (uint16_t)v[i].first;
-        p->merges[i] = (uint8_t)v[i].second;
-    }
-    return 0;
-}
+__device__ __forceinline__ int leaves_cap(int n) { return n / 56 + 2; }
+static inline int leaves_cap_host(long long n) { return (int)(n / 56 + 2); }
 
-__device__ __forceinline__ double pairwise_gather(const double* __restrict__ data, const int32_t* __restrict__ idx,
-                                                  const Program& prog) {
-    double stack[24];
-    int sp = 0;
-    long long pos = 0;
-    for (int l = 0; l < prog.n_leaves; ++l) {
-        const int n = prog.size[l];
-        const int32_t* ix = idx + pos;
-        double res;
-        if (n < 8) {
-            res = 0.0;
-            for (int i = 0; i < n; ++i) res += data[ix[i]];
+// leaves of pairwise_sum(n): size[l] (<= 128) and merges[l]; returns the count. One thread.
+__device__ int build_program(int n, uint8_t* size, uint8_t* merges) {
+    int stack_n[40];
+    uint8_t stack_m[40];
+    int sp = 0, nl = 0;
+    stack_n[sp] = n;
+    stack_m[sp++] = 0;
+    while (sp > 0) {
+        --sp;
+        const int s = stack_n[sp];
+        const int m = stack_m[sp];
+        if (s <= 128) {
+            size[nl] = (uint8_t)s;      // 128 fits
+            merges[nl++] = (uint8_t)m;
         } else {
-            double r0 = data[ix[0]], r1 = data[ix[1]], r2 = data[ix[2]], r3 = data[ix[3]];
-            double r4 = data[ix[4]], r5 = data[ix[5]], r6 = data[ix[6]], r7 = data[ix[7]];
-            int i = 8;
-            for (; i < n - (n % 8); i += 8) {
-                r0 += data[ix[i]];
-                r1 += data[ix[i + 1]];
-                r2 += data[ix[i + 2]];
-                r3 += data[ix[i + 3]];
-                r4 += data[ix[i + 4]];
-                r5 += data[ix[i + 5]];
-                r6 += data[ix[i + 6]];
-                r7 += data[ix[i + 7]];
-            }
-            res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
-            for (; i < n; ++i) res += data[ix[i]];
-        }
-        pos += n;
-        stack[sp++] = res;
-        for (int m = 0; m < prog.merges[l]; ++m) {
-            --sp;
-            stack[sp - 1] = stack[sp - 1] + stack[sp];
+            int n2 = s / 2;
+            n2 -= n2 % 8;
+            stack_n[sp] = s - n2;       // right half: finishes this node's merge and everything pending above it
+            stack_m[sp++] = (uint8_t)(m + 1);
+            stack_n[sp] = n2;           // left half first
+            stack_m[sp++] = 0;
         }
     }
-    return stack[0];
+    return nl;
+}
+
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+                 : "memory");
+}
+
+// sum of data[row[0 .. len)] in numpy's pairwise order; row = this CTA's first index row + seg_off
+template <bool DATA_SMEM>
+__device__ double pairwise_rows(const double* __restrict__ data, const int32_t* __restrict__ rows, long long ld, int n_rows,
+                                int len, bool vec_ok, const uint8_t* psize, const uint8_t* pmerge, int32_t* tiles) {
+    const int tid = threadIdx.x;
+    const int n_tiles = (len + GC - 1) / GC;
+    auto load_tile = [&](int t) {
+        int32_t* dst = tiles + (size_t)(t % GST) * GR * GC;
+        const int col0 = t * GC;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int r = (tid >> 3) + 16 * k, ch = tid & 7;
+            const int col = col0 + 4 * ch;
+            if (r < n_rows && col < len) {
+                const int32_t* src = rows + (long long)r * ld + col;
+                int32_t* d = dst + r * GC + ((ch ^ (r & 7)) << 2);
+                if (vec_ok && col + 4 <= len) {
+                    cp_async_16(d, src);
+                } else {
+                    const int m = min(4, len - col);
+                    for (int e = 0; e < m; ++e) cp_async_4(d + e, src + e);
+                }
+            }
+        }
+    };
+    for (int t = 0; t < GST - 1; ++t) {
+        if (t < n_tiles) load_tile(t);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    double stack[32];
+    int sp = 0, li = 0;
+    int full_left = psize[0] >> 3, tail = psize[0] & 7;
+    bool started = false;
+    double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0, res = 0.0;
+    const bool active = tid < n_rows;
+    for (int t = 0; t < n_tiles; ++t) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(GST - 2) : "memory");
+        __syncthreads();  // tile t is visible, everybody is done with tile t - 1
+        if (t + GST - 1 < n_tiles) load_tile(t + GST - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (!active) continue;
+        const int32_t* trow = tiles + (size_t)(t % GST) * GR * GC + tid * GC;
+        const int col0 = t * GC;
+#pragma unroll
+        for (int o = 0; o < GC / 8; ++o) {
+            const int col = col0 + 8 * o;
+            if (col >= len) break;
+            const int4 ia = *reinterpret_cast<const int4*>(trow + (((2 * o) ^ (tid & 7)) << 2));
+            const int4 ib = *reinterpret_cast<const int4*>(trow + (((2 * o + 1) ^ (tid & 7)) << 2));
+            if (full_left > 0) {
+                const double a0 = data[ia.x], a1 = data[ia.y], a2 = data[ia.z], a3 = data[ia.w];
+                const double a4 = data[ib.x], a5 = data[ib.y], a6 = data[ib.z], a7 = data[ib.w];
+                if (!started) {
+                    r0 = a0; r1 = a1; r2 = a2; r3 = a3; r4 = a4; r5 = a5; r6 = a6; r7 = a7;
+                    started = true;
+                } else {
+                    r0 += a0; r1 += a1; r2 += a2; r3 += a3; r4 += a4; r5 += a5; r6 += a6; r7 += a7;
+                }
+                if (--full_left > 0) continue;
+                res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+                if (tail > 0) continue;  // the leftovers of the last leaf follow in the next octet
+            } else {
+                // fewer than 8 elements: a leaf shorter than 8 (sequential from 0.0) or the leftovers of the last leaf
+                const int idx8[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+                if (!started) res = 0.0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (e < tail) res += data[idx8[e]];
+            }
+            // ---- the leaf is complete: push, merge, next leaf
+            stack[sp++] = res;
+            for (int m = pmerge[li]; m > 0; --m) {
+                --sp;
+                stack[sp - 1] = stack[sp - 1] + stack[sp];
+            }
+            ++li;
+            full_left = psize[li] >> 3;   // one sentinel entry follows the last leaf
+            tail = psize[li] & 7;
+            started = false;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // the ring is free for the next segment
+    return active ? stack[0] : 0.0;
 }
 
 // out[r] = mean(data[idx[r, 0:n1]])                       (n2 == 0, K4)
 // out[r] = | mean(data[idx[r, 0:n1]]) - mean(data[idx[r, n1:n1+n2]]) |   (n2 > 0, K5)
-__global__ void __launch_bounds__(128)
+template <bool DATA_SMEM>
+__global__ void __launch_bounds__(GR)
 gather_mean_kernel(const double* __restrict__ data, int n_data, const int32_t* __restrict__ idx, long long ld, int R,
-                   int n1, int n2, const __grid_constant__ Program p1, const __grid_constant__ Program p2,
-                   int data_in_smem, double* __restrict__ out) {
-    extern __shared__ double sm_data[];
+                   int n1, int n2, int vec1, int vec2, double* __restrict__ out) {
+    extern __shared__ __align__(16) uint8_t gsm[];
+    int32_t* tiles = reinterpret_cast<int32_t*>(gsm);                            // [GST][GR][GC]
+    uint8_t* prog = gsm + (size_t)GST * GR * GC * 4;
+    const int cap1 = leaves_cap(n1), cap2 = n2 > 0 ? leaves_cap(n2) : 0;
+    uint8_t* ps1 = prog;
+    uint8_t* pm1 = ps1 + cap1;
+    uint8_t* ps2 = pm1 + cap1;
+    uint8_t* pm2 = ps2 + cap2;
+    double* sm_data = reinterpret_cast<double*>(gsm + (((size_t)GST * GR * GC * 4 + 2 * (size_t)(cap1 + cap2) + 15) & ~size_t(15)));
     // blockIdx.y = batch entry (its own data vector, index rows and outputs): nine CIs of a row in one launch
     data += (long long)blockIdx.y * n_data;
     idx += (long long)blockIdx.y * R * ld;
     out += (long long)blockIdx.y * R;
+    if (threadIdx.x == 0) {
+        const int l1 = build_program(n1, ps1, pm1);
+        ps1[l1] = 0;                                  // sentinel read after the last leaf
+        if (n2 > 0) {
+            const int l2 = build_program(n2, ps2, pm2);
+            ps2[l2] = 0;
+        }
+    }
     const double* d = data;
-    if (data_in_smem) {
-        for (int i = threadIdx.x; i < n_data; i += blockDim.x) sm_data[i] = data[i];
-        __syncthreads();
+    if (DATA_SMEM) {
+        for (int i = threadIdx.x; i < n_data; i += GR) sm_data[i] = data[i];
         d = sm_data;
     }
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const int32_t* row = idx + (long long)r * ld;
-    const double m1 = pairwise_gather(d, row, p1) / (double)n1;
+    __syncthreads();
+    const int row0 = blockIdx.x * GR;
+    const int n_rows = min(GR, R - row0);
+    const int32_t* rows = idx + (long long)row0 * ld;
+    const double s1 = pairwise_rows<DATA_SMEM>(d, rows, ld, n_rows, n1, vec1 != 0, ps1, pm1, tiles);
+    double res = s1 / (double)n1;
     if (n2 > 0) {
-        const double m2 = pairwise_gather(d, row + n1, p2) / (double)n2;
-        out[r] = fabs(m1 - m2);
-    } else {
-        out[r] = m1;
+        const double s2 = pairwise_rows<DATA_SMEM>(d, rows + n1, ld, n_rows, n2, vec2 != 0, ps2, pm2, tiles);
+        res = fabs(res - s2 / (double)n2);
     }
+    if ((int)threadIdx.x < n_rows) out[row0 + threadIdx.x] = res;
 }
 
 }  // namespace stats
@@ -342,17 +427,24 @@ static int launch_gather_mean(const double* data, int n_data, const int32_t* idx
     MMX_REQUIRE(n1 >= 1 && n2 >= 0 && ld >= (int64_t)n1 + n2, "bad segment sizes");
     MMX_REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
     if (R == 0) return 0;
-    Program p1, p2;
-    if (make_program(n1, &p1) != 0) return -2;
-    p2.n_leaves = 0;
-    if (n2 > 0 && make_program(n2, &p2) != 0) return -2;
-    const int in_smem = (size_t)n_data * 8 <= 200 * 1024;
-    const size_t smem = in_smem ? (size_t)n_data * 8 : 0;
+    const size_t prog = 2 * (size_t)(leaves_cap_host(n1) + (n2 > 0 ? leaves_cap_host(n2) : 0));
+    const size_t base = (((size_t)GST * GR * GC * 4 + prog + 15) & ~size_t(15));
+    MMX_REQUIRE(base <= 200 * 1024, "vectors too long for the pairwise-sum program (n1=%d n2=%d)", n1, n2);
+    const bool in_smem = (size_t)n_data * 8 <= (size_t)DATA_SMEM_MAX && base + (size_t)n_data * 8 <= 200 * 1024;
+    const size_t smem = base + (in_smem ? (size_t)n_data * 8 : 0);
+    // 16-byte copies need every row segment to start on a 16-byte boundary
+    const bool al = (reinterpret_cast<uintptr_t>(idx) % 16 == 0) && (ld % 4 == 0) && ((int64_t)R * ld % 4 == 0);
+    const int vec1 = al ? 1 : 0, vec2 = (al && n1 % 4 == 0) ? 1 : 0;
     static const char gather_tag = 0;
-    if (smem > 48 * 1024 && first_use_on_device(&gather_tag))
-        MMX_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    gather_mean_kernel<<<dim3((R + 127) / 128, batch), 128, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, p1, p2,
-                                                                            in_smem, out);
+    if (first_use_on_device(&gather_tag)) {
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MMX_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    const dim3 grid((R + GR - 1) / GR, batch);
+    if (in_smem)
+        gather_mean_kernel<true><<<grid, GR, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, vec1, vec2, out);
+    else
+        gather_mean_kernel<false><<<grid, GR, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, vec1, vec2, out);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
