@@ -306,6 +306,7 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
             kept: dict = {}
             s_t2i = _maxsim_streamed(t2i_txt_embeds, img_embeds, dev, keep=kept)
             (i_flat, i_off), i_lens = kept["d"], img_embeds.lens
+            t_flat, t_off = kept["q"]
         else:
             i_flat, i_off, i_lens = _flatten_any(img_embeds, dev)
             t_flat, t_off, t_lens = _flatten_any(t2i_txt_embeds, dev)
@@ -326,6 +327,12 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
             for name, sc, (go, gi) in (("T2I", s_t2i, (id_off, id_idx)), ("I2T", s_i2t, (b_off, b_idx)),
                                        ("I2T_Sym", s_sym, (id_off, id_idx))):
                 out[name].ties = ops.exact_tie_counts(out[name], go, gi, scores=sc)
+            # tie class T6: where the zero row of pad_sequence (main.py:465) can win a maximum. The reference
+            # re-chunks the RESAMPLED lists in every bootstrap iteration, so a document's padding depends on the
+            # neighbours that were drawn; the bootstrap here keeps the base chunking's flags
+            out["T2I"].t6 = _t6_report(t_flat, t_off, i_flat, i_off, _pad_flags(i_lens), s_t2i, dev)
+            out["I2T"].t6 = _t6_report(i_flat, i_off, a_flat, a_off, fl_a, s_i2t, dev)
+            out["I2T_Sym"].t6 = dict(out["T2I"].t6, note="transposed T2I matrix (main.py:624): the T2I pairs, seen per image")
     else:
         img = _h2d(_as_bf16(img_embeds, "img_embeds"), dev)
         t2i = _h2d(_as_bf16(t2i_txt_embeds, "t2i_txt_embeds"), dev)
@@ -343,6 +350,28 @@ def score_and_rank(img_embeds, t2i_txt_embeds, all_txt_embeds, m_info: Dict, cap
                 out[name].ties = ops.exact_tie_counts(out[name], go, gi, Q=qq, G=gg)
     out["I2T"].col2unit = torch.arange(n * caps_per_img, dtype=torch.int32, device=dev) // caps_per_img
     return out
+
+
+def _t6_report(q_flat, q_off, d_flat, d_off, flags: np.ndarray, scores: torch.Tensor, dev: torch.device) -> Dict[str, int]:
+    """Tie class T6 as numbers. A (query, document) score depends on the document's zero-padding flag iff some query row
+    has no positive similarity with any row of the document (the padded zero then wins that row's maximum).
+    Two more K2 passes — every document padded / no document padded — find those pairs:
+      pairs_sensitive_to_padding    pairs whose score differs between the two (a re-chunked bootstrap iteration of the
+                                    reference, main.py:602-624, can move exactly these);
+      queries_sensitive_to_padding  queries (rows) with at least one such pair;
+      queries_with_clamped_maximum  rows that hold a clamped maximum against a document the BASE chunking pads — the
+                                    scores this library's bootstrap uses for every iteration;
+      documents_padded              documents the base chunking pads."""
+    nd = int(d_off.numel()) - 1
+    ones = torch.ones(nd, dtype=torch.uint8, device=dev)
+    s_pad = ops.maxsim_scores(q_flat, q_off, d_flat, d_off, ones)
+    s_raw = ops.maxsim_scores(q_flat, q_off, d_flat, d_off, None)
+    sens = s_pad != s_raw
+    base = (scores != s_raw) & sens                  # only padded documents can differ from the unpadded pass
+    return {"pairs_sensitive_to_padding": int(sens.sum().item()),
+            "queries_sensitive_to_padding": int(sens.any(dim=1).sum().item()),
+            "queries_with_clamped_maximum": int(base.any(dim=1).sum().item()),
+            "documents_padded": int(np.asarray(flags).sum())}
 
 
 def base_metrics(ranks: Dict[str, ops.ProtocolRanks]) -> Dict[str, float]:
@@ -466,12 +495,32 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     if drng is None:
         caps = t2i_captions if t2i_captions is not None else [""] * n_images
         caption_table = None
-    aggregated["_failure_analysis"] = aggregate_failure_from_hits(caps, hits, drawn, table=caption_table)  # main.py:664
+    aggregated["_failure_analysis"] = aggregate_failure_from_hits(                                      # main.py:664
+        caps, hits, drawn, first_seen_order=_first_seen_order(sample_indices, n_images), table=caption_table)
     aggregated["_bootstrap_values"] = {k: values[:, j].copy() for j, k in enumerate(METRIC_KEYS)}
     aggregated["_base_metrics"] = base_metrics(ranks)
     if tie_report:
         aggregated["_tie_report"] = {name: ops.tie_summary(ranks[name]) for name in ("T2I", "I2T", "I2T_Sym")}
+        if m_info["type"] == "colpali":
+            for name in ("T2I", "I2T", "I2T_Sym"):
+                aggregated["_tie_report"][name]["T6"] = ranks[name].t6
     return aggregated
+
+
+def _first_seen_order(sample_indices, n_images: int) -> np.ndarray:
+    """Base query indices in the order the reference's flattened per-iteration record list first meets them
+    (main.py:634,669-722: iteration 0 in sample order, then iteration 1, ...): the insertion order of
+    ``accuracy_by_category`` in the ``_failure_analysis`` cell. Only the leading iterations are read back (all of them
+    for small problems); queries they never drew follow in index order."""
+    B = int(sample_indices.shape[0])
+    rows = B if B * n_images <= (1 << 20) else min(B, 8)
+    head = sample_indices[:rows]
+    head = head.cpu().numpy() if isinstance(head, torch.Tensor) else np.asarray(head)
+    flat = head.reshape(-1).astype(np.int64)
+    _, first = np.unique(flat, return_index=True)
+    seen = flat[np.sort(first)]
+    rest = np.setdiff1d(np.arange(n_images, dtype=np.int64), seen, assume_unique=False)
+    return np.concatenate([seen, rest])
 
 
 class FlatMultiVector:

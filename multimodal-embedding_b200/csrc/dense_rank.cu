@@ -96,7 +96,8 @@ __device__ __forceinline__ int tile_id(const Params& p, int i) {
 }
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-    if (v >= 0.0f)
+    // by sign BIT: -0.0 compares >= 0 but its pattern is INT_MIN, which a signed max would lose against -inf
+    if (__float_as_int(v) >= 0)
         atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
     else
         atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));

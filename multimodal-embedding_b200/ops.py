@@ -56,6 +56,7 @@ class ProtocolRanks:
     q_unit: Optional[torch.Tensor] = None
     scores: Optional[torch.Tensor] = None
     ties: Optional[torch.Tensor] = None       # [nq] int32 non-GT columns scoring EXACTLY the threshold (tie class T2)
+    t6: Optional[dict] = None                 # ColPali: how many scores depend on pad_sequence's zero row (tie class T6)
     top_s: Optional[torch.Tensor] = None      # [nq, k] fp32 top-k scores (KT), higher first, ties by lower column
     top_i: Optional[torch.Tensor] = None      # [nq, k] int32 global column ids, -1 = padding
     # LIST mode (galleries whose bitmask does not fit): bits is None and the above-GT sets are kept as

@@ -820,6 +820,68 @@ def test_run_bootstrap_colpali_small(mmx_mod):
     assert np.array_equal(got, oracle.bootstrap_identity(sets, si, n))
 
 
+def test_colpali_bootstrap_vs_reference_literal_loop(mmx_mod, golden_dir):
+    """run_bootstrap_from_embeddings on ragged ColPali lists against the reference's LITERAL loop (main.py:586-634: the
+    resampled lists are re-chunked and re-padded in every iteration — tie class T6), as computed by the reference's own
+    functions (golden colpali_boot.npz) and by oracle.bootstrap_rescore_reference(colpali=True): all nine metrics of all
+    12 iterations, the base metrics, and T6 as numbers (1573 (image, caption) scores hold a clamped maximum)."""
+    z = np.load(golden_dir / "colpali_boot.npz")
+    docs = list(from_bits(z["docs"], 128).split([int(l) for l in z["doc_lens"]]))
+    caps = list(from_bits(z["caps"], 128).split([int(l) for l in z["cap_lens"]]))
+    n, B = len(docs), int(z["sample_indices"].shape[0])
+    keys = [str(k) for k in z["metric_keys"]]
+    m_info = {"type": "colpali", "name": "ColSynth"}
+    row = mmx_mod.run_bootstrap_from_embeddings(docs, caps[0::5], caps, m_info, B, rng=np.random.RandomState(42),
+                                                tie_report=True)
+    assert [row["_base_metrics"][k] for k in keys] == list(z["base_metrics"])
+    got = np.stack([row["_bootstrap_values"][k] for k in keys], axis=1)
+    assert np.array_equal(got, z["boot_metrics"])
+    lit = oracle.bootstrap_rescore_reference(docs, caps[0::5], caps, B, colpali=True, rng=np.random.RandomState(42))
+    assert np.array_equal(got, np.array([[m[k] for k in keys] for m in lit]))
+    # scores within tolerance of the reference's
+    ranks = mmx_mod.score_and_rank(docs, caps[0::5], caps, m_info, want_ties=True)
+    t6 = ranks["I2T"].t6
+    assert t6 == {"pairs_sensitive_to_padding": 1573, "queries_sensitive_to_padding": 42,
+                  "queries_with_clamped_maximum": 42, "documents_padded": 181}
+    assert ranks["T2I"].t6["pairs_sensitive_to_padding"] == 0 and ranks["T2I"].t6["documents_padded"] == 0
+    assert row["_tie_report"]["I2T"]["T6"] == t6
+    for name in ("T2I", "I2T", "I2T_Sym"):
+        assert row["_tie_report"][name]["queries_with_exact_ties"] == 0
+
+
+def test_permutation_test_per_query_vectors_n50000(mmx_mod):
+    """configs[4]: permutation_test on the per-query vectors of two 25 000-query models (n1 = n2 = 25 000, 0/1 hits),
+    shuffles replayed on the device (K6s long path) — same p-value and same numpy generator state as main.py:281-302
+    run on the host."""
+    rs = np.random.RandomState(11)
+    d1 = (rs.rand(25000) < 0.47).astype(np.float64)
+    d2 = (rs.rand(25000) < 0.46).astype(np.float64)
+    P = 300
+    g_dev, g_ref = np.random.RandomState(42), np.random.RandomState(42)
+    p_dev = mmx_mod.permutation_test(d1, d2, P, rng=g_dev)
+    p_ref = oracle.permutation_test(d1, d2, P, rng=g_ref)
+    assert p_dev == p_ref
+    assert g_dev.randint(0, 1 << 30, size=4).tolist() == g_ref.randint(0, 1 << 30, size=4).tolist()
+    # general doubles (rank vectors), unequal lengths, n not a multiple of 4 (scalar index copies in K5)
+    e1, e2 = rs.normal(5.0, 2.0, size=20001), rs.normal(5.02, 2.0, size=17000)
+    p_dev = mmx_mod.permutation_test(e1, e2, 60, rng=g_dev)
+    p_ref = oracle.permutation_test(e1, e2, 60, rng=g_ref)
+    assert p_dev == p_ref
+    assert g_dev.randint(0, 1 << 30) == g_ref.randint(0, 1 << 30)
+
+
+@pytest.mark.parametrize("n1,n2", [(40000, 25536), (33000, 1), (1, 40000), (50000, 15000)])
+def test_perm_stats_long_vectors_bit_exact(mmx_mod, n1, n2):
+    """K5 on vectors far beyond the old 320-leaf limit of the pairwise-sum program."""
+    dev = _dev()
+    rs = np.random.RandomState(n1 + n2)
+    data = rs.rand(n1 + n2) * 100
+    perm = np.stack([rs.permutation(n1 + n2) for _ in range(9)]).astype(np.int32)
+    d = mmx_mod.ops.perm_stats(torch.from_numpy(data).to(dev), n1, torch.from_numpy(perm).to(dev)).cpu().numpy()
+    w = np.array([np.abs(np.mean(data[perm[p]][:n1]) - np.mean(data[perm[p]][n1:])) for p in range(9)])
+    assert np.array_equal(d, w)
+
+
 def test_run_bootstrap_benchmark_reference_signature(mmx_mod):
     """main.py:478-667 through the drop-in signature, with stand-ins for the upstream pieces it keeps (dataset walk,
     image cache, encoders): items without an image or with fewer than five captions are skipped exactly like

@@ -100,6 +100,32 @@ def test_bootstrap_rescore_and_identity(dense):
     assert np.array_equal(100.0 * correct / N, z["boot_metrics"])
 
 
+def test_colpali_bootstrap_literal_loop(golden_dir):
+    """The ColPali branch of main.py:586-634 (lists, per-iteration re-chunking: tie class T6), as computed by the
+    reference's own compute_similarity_scores / compute_metrics_detailed (tests/golden/make_golden_colpali_boot.py):
+    the oracle's literal loop reproduces it, and so does the multiplicity identity evaluated with the BASE chunking's
+    padding — on a problem where 1573 (image, caption) scores depend on the padded zero row."""
+    z = np.load(golden_dir / "colpali_boot.npz")
+    docs = list(from_bits(z["docs"], 128).split([int(l) for l in z["doc_lens"]]))
+    caps = list(from_bits(z["caps"], 128).split([int(l) for l in z["cap_lens"]]))
+    n, si = len(docs), z["sample_indices"]
+    keys = [str(k) for k in z["metric_keys"]]
+    assert keys == oracle.METRIC_KEYS
+    assert np.array_equal(np.random.RandomState(42).randint(0, n, size=si.shape), si)
+    per = oracle.bootstrap_rescore_reference(docs, caps[0::5], caps, len(si), colpali=True, sample_indices=si)
+    assert np.array_equal(np.array([[m[k] for k in keys] for m in per]), z["boot_metrics"])
+    s_t2i, s_i2t = oracle.maxsim_scores(caps[0::5], docs), oracle.maxsim_scores(docs, caps)
+    assert np.array_equal(s_t2i.numpy(), z["scores_t2i"]) and np.array_equal(s_i2t.numpy(), z["scores_i2t"])
+    sets = {}
+    for name, s, gt, cu in (("T2I", s_t2i, [[i] for i in range(n)], np.arange(n)),
+                            ("I2T", s_i2t, [list(range(5 * i, 5 * i + 5)) for i in range(n)], np.arange(5 * n) // 5),
+                            ("I2T_Sym", s_t2i.t().contiguous(), [[i] for i in range(n)], np.arange(n))):
+        thr, _, tied = oracle.above_gt_counts(s, gt)
+        assert int(tied.sum()) == 0
+        sets[name] = ((s > thr[:, None]).numpy(), cu, np.arange(n))
+    assert np.array_equal(100.0 * oracle.bootstrap_identity(sets, si, n) / n, z["boot_metrics"])
+
+
 def test_ci_and_std(golden_dir):
     z = np.load(golden_dir / "stats.npz")
     data = z["ci_data"]
