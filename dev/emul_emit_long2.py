@@ -1,6 +1,7 @@
 """numpy emulation of emit_long_kernel v2 (csrc/shuffle.cu): one CTA of T threads, every thread owns S consecutive
-words of the epoch's window (S odd), Gauss-Seidel inside a segment (the running brackets l <= a(t) <= u are updated
-word by word), Jacobi across segments (one block-wide scan of the packed (l, u) counts per round), convergence =
+words of the epoch's window (S odd); the accepts of a segment are non-increasing in the number of accepts behind it,
+so a run from the upper base Ub bounds them from below and a run from the lower base Lb from above; one block-wide scan
+of the packed counts per round gives the next bases (Jacobi across segments), convergence =
 every thread whose lower base is below the epoch's step count has an exact base. Checked against numpy's shuffle
 (permutations and stream position) before the kernel first ran on a GPU.
 
@@ -50,20 +51,29 @@ def epoch(words, pos, n_words, i_hi, c, M, W0, stats):
         Lb = np.zeros(T, dtype=np.int64)
         Ub = np.minimum(t0, W)
         rnd = 0
+        lens = np.clip(W - t0, 0, S)
+        have_cnt = np.zeros(T, dtype=bool)               # frozen segments: the two runs accepted the same words
+        cnt = np.zeros(T, dtype=np.int64)
         while True:
-            l, u = Lb.copy(), Ub.copy()
+            lo, hi = Ub.copy(), Lb.copy()                   # two independent runs: from the upper and the lower base
             for s in range(S):
-                a1 = (v[:, s] + u) <= i_hi
-                a2 = (v[:, s] + l) <= i_hi
-                l += a1
-                u += a2
-            pred = (Lb >= c) | (Lb == Ub) | (t0 >= W)
+                lo += (v[:, s] + lo) <= i_hi
+                hi += (v[:, s] + hi) <= i_hi
+            cl, cu = lo - Ub, hi - Lb                        # accepts are non-increasing in the start value
+            cl = np.where(have_cnt, cnt, cl)                 # (the kernel does not walk frozen segments again)
+            cu = np.where(have_cnt, cnt, cu)
+            newly = (~have_cnt) & (cl == cu) & (Lb < c)
+            cnt = np.where(newly, cl, cnt)
+            have_cnt |= newly
+            behind = Lb >= c                                 # behind the epoch's end: (0, len) is a valid bracket
+            cl = np.where(behind, 0, cl)
+            cu = np.where(behind, lens, cu)
+            assert (cl <= cu).all()
+            pred = (Lb >= c) | (Lb == Ub) | (lens == 0)
             if pred.all():
                 break
-            cl, cu = l - Lb, u - Ub
-            assert (cl <= cu).all()
-            Lb = np.cumsum(cl) - cl
-            Ub = np.cumsum(cu) - cu
+            Lb = np.maximum(Lb, np.cumsum(cl) - cl)          # keep the brackets nested
+            Ub = np.minimum(Ub, np.cumsum(cu) - cu)
             rnd += 1
             assert rnd <= T
         stats.append(rnd)

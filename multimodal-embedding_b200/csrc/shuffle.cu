@@ -40,12 +40,27 @@ constexpr int MAX_N = 16384;   // B/C/D: work grows with n * |W| (~n^2 P); longe
 constexpr int MAX_N_LONG = 65536;   // LONG emit: masked values fit uint16
 constexpr int LT = 1024;            // threads of the LONG emit CTA
 
+constexpr int SERIAL_BELOW = 512;       // LONG emit: steps with i < 512 are replayed by one warp, 32 words at a time
+constexpr int MAX_EPOCHS = 20;
+// mask epochs of the LONG emit's bracket scheme: bit lengths of n - 1 down to that of SERIAL_BELOW
+static int long_epochs(int n) {
+    int e = 0;
+    for (int i_hi = n - 1; i_hi >= SERIAL_BELOW && e < MAX_EPOCHS;) {
+        int b = 0;
+        while ((1ll << b) <= i_hi) ++b;
+        i_hi = std::max(1 << (b - 1), SERIAL_BELOW) - 1;
+        ++e;
+    }
+    return e;
+}
+
 struct Plan {
     long long n_chunks, steps;
     int n_blocks, pb;
     bool long_n, lists_in_smem, rows_in_smem;
     int apply_grid;
-    size_t off_tab, off_m, off_s, off_j, off_arr, off_pi, off_c, off_d, off_g, off_l, total;
+    int n_ep;
+    size_t off_tab, off_m, off_s, off_j, off_arr, off_pi, off_c, off_d, off_g, off_l, off_rm, off_rb, off_eh, total;
 };
 
 constexpr size_t SMEM_MAX = 227 * 1024;
@@ -74,6 +89,13 @@ static Plan make_plan(int n, int P, long long n_words) {
     pl.off_d = o;   o += up((size_t)(pl.n_blocks + 1) * n * 4);   // prefixes of the block composites
     pl.off_g = o;   o += up(pl.long_n && !pl.rows_in_smem ? (size_t)(pl.n_blocks + 1) * 2 * n * 4 : 0);  // rows in L2
     pl.off_l = o;   o += up(pl.long_n && !pl.lists_in_smem ? (size_t)pl.apply_grid * n * 2 : 0);        // step lists in L2
+    // LONG emit records: per (permutation, epoch, thread) the accept mask and the exact base, per (permutation, epoch)
+    // the window's first word and its geometry — the j values are extracted from them by all SMs afterwards
+    pl.n_ep = pl.long_n ? long_epochs(n) : 0;
+    const size_t recs = (size_t)P * pl.n_ep;
+    pl.off_rm = o;  o += up(recs * LT * 8);
+    pl.off_rb = o;  o += up(recs * LT * 2);
+    pl.off_eh = o;  o += up(recs * 16);
     pl.total = o;
     return pl;
 }
@@ -253,9 +275,11 @@ emit_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, long 
 // permutation (masks below 64: a handful of words each) are walked by one thread.
 constexpr int RING = 57344;             // words of the ring (224 KB)
 constexpr int WCAP = RING - 8;          // longest window of one epoch
-constexpr int SERIAL_BELOW = 64;        // steps with i < 64 are walked by thread 0
-constexpr int TAIL_W = 4096;            // words the serial tail may look at
-constexpr int MAX_EPOCHS = 20;
+constexpr int TAIL_W = 4096;            // words the warp tail may look at
+#ifndef MMX_S_MIN
+#define MMX_S_MIN 1
+#endif
+constexpr int S_MIN = MMX_S_MIN;        // fewest words per thread: small epochs run on few warps (cheaper rounds)
 
 struct LongEpoch {
     int i_hi, c, W0;
@@ -301,9 +325,79 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+#ifdef MMX_EMIT_TIMING
+// dev/emit_timing.cu: cycles per epoch and phase, accumulated by thread 0  [epoch][stage, rounds, emit, #rounds]
+__device__ long long g_emit_prof[MAX_EPOCHS + 1][4];
+__device__ long long g_emit_round[MAX_EPOCHS + 1][4];   // thread 0, summed over rounds: walk, scan, barrier, base
+#define EMIT_RADD(ep, k, val) \
+    if (threadIdx.x == 0) g_emit_round[ep][k] += (val)
+#define EMIT_CLOCK(v) const long long v = clock64()
+#define EMIT_ADD(ep, k, val) \
+    if (threadIdx.x == 0) g_emit_prof[ep][k] += (val)
+#else
+#define EMIT_CLOCK(v)
+#define EMIT_ADD(ep, k, val)
+#define EMIT_RADD(ep, k, val)
+#endif
+
+// barrier 1 over the first `nthreads` threads of the CTA (a multiple of 32) with an AND reduction of `pred`
+__device__ __forceinline__ int bar_and_active(int pred, int nthreads) {
+    int r;
+    asm volatile(
+        "{\n .reg .pred p, q;\n setp.ne.s32 q, %1, 0;\n barrier.cta.red.and.pred p, 1, %2, q;\n selp.s32 %0, 1, 0, p;\n}"
+        : "=r"(r)
+        : "r"(pred), "r"(nthreads)
+        : "memory");
+    return r;
+}
+
+// accepts of a run of words that starts with `a` accepts behind it: word accepted iff a <= i_hi - v
+__device__ __forceinline__ int walk_count(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int a) {
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) {
+        const int d = i_hi - (int)(w[k] & M);
+        a += (a <= d) ? 1 : 0;
+    }
+    return a;
+}
+// two independent runs at once (the lower and the upper end of a bracket)
+__device__ __forceinline__ void walk_count2(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int& a, int& b) {
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) {
+        const int d = i_hi - (int)(w[k] & M);
+        a += (a <= d) ? 1 : 0;
+        b += (b <= d) ? 1 : 0;
+    }
+}
+// two runs, recording which words the first one accepted (bit k0 + k of m)
+__device__ __forceinline__ void walk_count2_mask(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int& a, int& b,
+                                                 int k0, unsigned long long& m) {
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) {
+        const int d = i_hi - (int)(w[k] & M);
+        const int acc = (a <= d) ? 1 : 0;
+        a += acc;
+        b += (b <= d) ? 1 : 0;
+        m |= (unsigned long long)acc << (k0 + k);
+    }
+}
+// the exact run: also records which words were accepted (bit k0 + k of m)
+__device__ __forceinline__ int walk_mask(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int a, int k0,
+                                         unsigned long long& m) {
+#pragma unroll 4
+    for (int k = 0; k < n; ++k) {
+        const int d = i_hi - (int)(w[k] & M);
+        const int acc = (a <= d) ? 1 : 0;
+        a += acc;
+        m |= (unsigned long long)acc << (k0 + k);
+    }
+    return a;
+}
+
 __global__ void __launch_bounds__(LT, 1)
 emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, int P,
-                 const __grid_constant__ LongPlan plan, long long* __restrict__ info, int32_t* __restrict__ jout) {
+                 const __grid_constant__ LongPlan plan, long long* __restrict__ info, int32_t* __restrict__ jout,
+                 unsigned long long* __restrict__ rmask, uint16_t* __restrict__ rbase, long long* __restrict__ ehead) {
     extern __shared__ uint32_t ring[];  // [RING] word g of the stream sits at ring[g % RING]
     __shared__ uint32_t wtot[2][LT / 32];
     __shared__ int s_end;
@@ -311,7 +405,7 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
     n_words &= ~3ll;                    // 16-byte copies only
     long long pos = 0;                  // first word not consumed yet
     long long loaded = 0;               // words [.., loaded) are in the ring or on their way
-    int pos_mod = 0;                    // pos % RING
+    int pos_mod = 0, loaded_mod = 0;    // pos % RING, loaded % RING
     int err = 0;
 
     // refill the ring up to pos + RING (the slots of consumed words), wait until [pos, pos + W) has landed
@@ -321,13 +415,17 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
         const long long until_prev = loaded;
         const long long until = min(n_words, (pos + RING) & ~3ll);
         if (until > loaded) {
-            long long g = loaded + 4ll * tid;
-            int r = (int)(g % RING);
-            for (; g < until; g += 4ll * LT) {
-                cp_async16(ring + r, words + g);
+            const int cnt = (int)(until - loaded);
+            int r = loaded_mod + 4 * tid;
+            if (r >= RING) r -= RING;
+            const uint32_t* src = words + loaded + 4 * tid;
+            for (int g = 4 * tid; g < cnt; g += 4 * LT) {
+                cp_async16(ring + r, src);
+                src += 4 * LT;
                 r += 4 * LT;
                 if (r >= RING) r -= RING;
             }
+            loaded_mod = (loaded_mod + cnt) % RING;
             loaded = until;
         }
         cp_async_commit();
@@ -348,77 +446,113 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
                     err = -1;
                     break;
                 }
+                EMIT_CLOCK(tc0);
                 stage(W);
-                int S = (W + LT - 1) / LT;
+                EMIT_CLOCK(tc1);
+                EMIT_ADD(e, 0, tc1 - tc0);
+                int S = max((W + LT - 1) / LT, S_MIN);
                 S |= 1;  // odd: the threads of a warp walk distinct banks
-                const int t0 = min(W, tid * S), len = min(W, t0 + S) - t0;
-                int r0 = pos_mod + t0;
-                if (r0 >= RING) r0 -= RING;
-                const int len1 = min(len, RING - r0);  // words before the ring wraps
-                int Lb = 0, Ub = t0;
-                int walked = -1, wl = 0;  // exact base of the last single-chain walk and its count
-                for (int rnd = 0;; ++rnd) {
-                    uint32_t pk;
-                    if (Lb == Ub) {
-                        if (walked != Lb) {  // exact base: the walk is the serial simulation of the segment
-                            int l = Lb;
-                            for (int k = 0; k < len1; ++k) l += ((int)(ring[r0 + k] & M) + l <= i_hi) ? 1 : 0;
-                            for (int k = len1; k < len; ++k) l += ((int)(ring[r0 + k - RING] & M) + l <= i_hi) ? 1 : 0;
-                            walked = Lb;
-                            wl = l - Lb;
+                const int n_act = (((W + S - 1) / S + 31) >> 5) << 5;  // threads that own words, whole warps
+                if (tid < n_act) {
+                    const int t0 = min(W, tid * S), len = min(W, t0 + S) - t0;
+                    int r0 = pos_mod + t0;
+                    if (r0 >= RING) r0 -= RING;
+                    const int len1 = min(len, RING - r0);  // words before the ring wraps
+                    const uint32_t* w1 = ring + r0;
+                    const uint32_t* w2 = ring + (r0 + len1 - RING);  // == ring when the segment wraps
+                    int Lb = 0, Ub = t0, cnt = 0;
+                    bool have_cnt = false, have_mask = false;  // the segment's accept count / accept mask is final
+                    unsigned long long acc_mask = 0;
+                    for (int rnd = 0;; ++rnd) {
+                        EMIT_CLOCK(ra);
+                        uint32_t pk;  // low half: a lower bound of this segment's accepts, high half: an upper bound
+                        if (Lb >= c) {
+                            pk = (uint32_t)len << 16;  // behind the epoch's end: nothing depends on it
+                        } else if (have_cnt) {
+                            pk = (uint32_t)cnt | ((uint32_t)cnt << 16);
+                        } else if (Lb == Ub) {  // exact base: the walk is the serial simulation of the segment
+                            acc_mask = 0;
+                            int a = walk_mask(w1, len1, M, i_hi, Lb, 0, acc_mask);
+                            a = walk_mask(w2, len - len1, M, i_hi, a, len1, acc_mask);
+                            cnt = a - Lb;
+                            have_cnt = have_mask = true;
+                            pk = (uint32_t)cnt | ((uint32_t)cnt << 16);
+                        } else {
+                            // accepts are non-increasing in the start value: a run from Ub bounds them from below, a
+                            // run from Lb from above. A run from anywhere in between stays between the two, so when
+                            // they accept the same number of words they accept the SAME words, and so does every run
+                            // from a narrower bracket: the segment's count (and mask) is final from then on
+                            int lo = Ub, hi = Lb;
+                            if (rnd >= 2) {  // brackets are narrow by now: most segments freeze here, keep the mask
+                                acc_mask = 0;
+                                walk_count2_mask(w1, len1, M, i_hi, lo, hi, 0, acc_mask);
+                                walk_count2_mask(w2, len - len1, M, i_hi, lo, hi, len1, acc_mask);
+                            } else {
+                                walk_count2(w1, len1, M, i_hi, lo, hi);
+                                walk_count2(w2, len - len1, M, i_hi, lo, hi);
+                            }
+                            pk = (uint32_t)(lo - Ub) | ((uint32_t)(hi - Lb) << 16);
+                            if (lo - Ub == hi - Lb) {
+                                cnt = hi - Lb;
+                                have_cnt = true;
+                                have_mask = rnd >= 2;
+                            }
                         }
-                        pk = (uint32_t)wl | ((uint32_t)wl << 16);
-                    } else {
-                        int l = Lb, u = Ub;
-                        for (int k = 0; k < len1; ++k) {
-                            const int v = (int)(ring[r0 + k] & M);
-                            const int a1 = (v + u <= i_hi) ? 1 : 0, a2 = (v + l <= i_hi) ? 1 : 0;
-                            l += a1;
-                            u += a2;
-                        }
-                        for (int k = len1; k < len; ++k) {
-                            const int v = (int)(ring[r0 + k - RING] & M);
-                            const int a1 = (v + u <= i_hi) ? 1 : 0, a2 = (v + l <= i_hi) ? 1 : 0;
-                            l += a1;
-                            u += a2;
-                        }
-                        pk = (uint32_t)(l - Lb) | ((uint32_t)(u - Ub) << 16);
-                    }
-                    uint32_t incl = pk;  // inclusive scan of both counts at once (each stays below 2^16)
+                        EMIT_CLOCK(rb);
+                        uint32_t incl = pk;  // inclusive scan of both counts at once (each stays below 2^16)
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += t;
-                    }
-                    if (lane == 31) wtot[rnd & 1][warp] = incl;
-                    const int settled = (Lb >= c) || (Lb == Ub) || (len == 0);
-                    if (__syncthreads_and(settled)) break;
-                    uint32_t ws = wtot[rnd & 1][lane];
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t t = __shfl_up_sync(0xffffffffu, ws, o);
-                        if (lane >= o) ws += t;
-                    }
-                    uint32_t base = __shfl_sync(0xffffffffu, ws, (warp + 31) & 31);
-                    if (warp == 0) base = 0;
-                    base += incl - pk;
-                    Lb = (int)(base & 0xffffu);
-                    Ub = (int)(base >> 16);
-                }
-                // ---- emit: the k-th accepted word of the epoch is the j of step i_hi - k
-                if (Lb < c) {
-                    int32_t* out = jp + (n - 1 - i_hi);
-                    int l = Lb;
-                    for (int k = 0; k < len && l < c; ++k) {
-                        const int r = r0 + k;
-                        const int v = (int)(ring[r >= RING ? r - RING : r] & M);
-                        if (v + l <= i_hi) {
-                            out[l] = v;
-                            if (++l == c) s_end = t0 + k + 1;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                            if (lane >= o) incl += t;
                         }
+                        if (lane == 31) wtot[rnd & 1][warp] = incl;
+                        const int settled = (Lb >= c) || (Lb == Ub) || (len == 0);
+                        EMIT_CLOCK(rc);
+                        const int all_settled = bar_and_active(settled, n_act);
+                        EMIT_CLOCK(rd);
+                        EMIT_RADD(e, 0, rb - ra);
+                        EMIT_RADD(e, 1, rc - rb);
+                        EMIT_RADD(e, 2, rd - rc);
+                        if (all_settled) break;
+                        const uint32_t base = __reduce_add_sync(0xffffffffu, lane < warp ? wtot[rnd & 1][lane] : 0u)
+                                              + incl - pk;
+                        Lb = max(Lb, (int)(base & 0xffffu));  // every round's bounds are valid: keep the brackets nested
+                        Ub = min(Ub, (int)(base >> 16));
+                        EMIT_ADD(e, 3, 1);
+                        EMIT_CLOCK(re);
+                        EMIT_RADD(e, 3, re - rd);
+                    }
+                    EMIT_CLOCK(tc2);
+                    EMIT_ADD(e, 1, tc2 - tc1);
+                    if (Lb < c && !have_mask) {  // frozen before the masks were kept: one exact walk
+                        acc_mask = 0;
+                        int a = walk_mask(w1, len1, M, i_hi, Lb, 0, acc_mask);
+                        a = walk_mask(w2, len - len1, M, i_hi, a, len1, acc_mask);
+                        cnt = a - Lb;
+                    }
+                    // ---- record: the j values themselves (the k-th accepted word of the epoch is the j of step
+                    // i_hi - k) are pulled out of the word stream by all SMs afterwards (extract_long_kernel) from this
+                    // thread's accept mask and exact base — 10 coalesced bytes instead of ~20 scattered stores
+                    {
+                        const size_t rec = ((size_t)p * plan.n_epochs + e) * LT + tid;
+                        rmask[rec] = acc_mask;
+                        rbase[rec] = (uint16_t)min(Lb, 0xffff);
+                        if (tid == 0) {
+                            ehead[2 * ((size_t)p * plan.n_epochs + e)] = pos;
+                            ehead[2 * ((size_t)p * plan.n_epochs + e) + 1] = (long long)S | ((long long)n_act << 32);
+                        }
+                    }
+                    if (Lb < c && Lb + cnt >= c) {  // this segment holds the epoch's last accept
+                        int need = c - Lb, k = 0;
+                        for (;; ++k)
+                            if ((acc_mask >> k) & 1ull)
+                                if (--need == 0) break;
+                        s_end = t0 + k + 1;
                     }
                 }
                 __syncthreads();
+                EMIT_CLOCK(tc3);
+                EMIT_ADD(e, 2, tc3 - tc1);
                 const int end = s_end;
                 if (end >= 0) {
                     pos += end;
@@ -435,25 +569,51 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
             }
         }
         if (err) break;
-        // ---- serial tail: the steps i < SERIAL_BELOW
+        // ---- warp tail: the steps i < SERIAL_BELOW (about 1.45 words each), 32 words at a time by warp 0. Lane k's word
+        // serves step i - (accepts among the lanes before it): the accept bits are the fixed point of
+        //     A = ballot( (w & mask(i - popc(A & lanes_before))) <= i - popc(A & lanes_before) ),
+        // reached from any start because lane k only depends on lanes < k (a few rounds; the masks change with i, so
+        // this also walks across the mask epochs below 512 without any staging)
         if (plan.i_tail >= 1) {
             const int W = (int)min((long long)TAIL_W, n_words - pos);
+            EMIT_CLOCK(tt0);
             stage(W);
-            if (tid == 0) {
-                int i = plan.i_tail, k = 0;
-                int32_t* out = jp + (n - 1);
-                for (; k < W && i >= 1; ++k) {
-                    const int r = pos_mod + k;
-                    const uint32_t mask = 0xffffffffu >> __clz(i);
-                    const int v = (int)(ring[r >= RING ? r - RING : r] & mask);
-                    if (v <= i) {
-                        out[-i] = v;
-                        --i;
+            EMIT_CLOCK(tt1);
+            EMIT_ADD(MAX_EPOCHS, 0, tt1 - tt0);
+            if (warp == 0) {
+                const uint32_t lanes_before = (1u << lane) - 1u;
+                int i = plan.i_tail, k0 = 0, end = -1;
+                while (i >= 1 && k0 + 32 <= W) {
+                    const int r = pos_mod + k0 + lane;
+                    const uint32_t w = ring[r >= RING ? r - RING : r];
+                    uint32_t A = 0xffffffffu, prevA;
+                    uint32_t v = 0;
+                    int il, acc;
+                    do {
+                        prevA = A;
+                        il = i - __popc(A & lanes_before);
+                        acc = 0;
+                        if (il >= 1) {
+                            v = w & (0xffffffffu >> __clz(il));
+                            acc = v <= (uint32_t)il;
+                        }
+                        A = __ballot_sync(0xffffffffu, acc);
+                    } while (A != prevA);
+                    if (acc) jp[n - 1 - il] = (int32_t)v;
+                    const int tot = __popc(A);
+                    if (tot >= i) {  // the permutation's last step (i = 1) was served by the highest accepting lane
+                        end = k0 + (31 - __clz(A)) + 1;
+                        i = 0;
+                    } else {
+                        i -= tot;
+                        k0 += 32;
                     }
                 }
-                s_end = (i == 0) ? k : -1;
+                if (lane == 0) s_end = end;
             }
             __syncthreads();
+            EMIT_CLOCK(tt2);
+            EMIT_ADD(MAX_EPOCHS, 2, tt2 - tt1);
             const int end = s_end;
             if (end < 0) {
                 err = (W >= TAIL_W) ? -3 : -1;
@@ -467,6 +627,37 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
     if (tid == 0) {
         info[0] = err ? -1 : 0;
         info[1] = err ? err : pos;  // exactly this many words were consumed
+    }
+}
+
+// D-long, second half: the j values of the bracket epochs from the records of emit_long_kernel. One CTA per
+// (permutation, epoch); thread t re-reads its segment's accepted words (bit k of its mask = word t S + k of the window)
+// and writes them from its exact base on. All SMs, HBM/L2-bound.
+__global__ void __launch_bounds__(LT)
+extract_long_kernel(const uint32_t* __restrict__ words, int n, const __grid_constant__ LongPlan plan,
+                    const long long* __restrict__ info, const unsigned long long* __restrict__ rmask,
+                    const uint16_t* __restrict__ rbase, const long long* __restrict__ ehead, int32_t* __restrict__ jout) {
+    if (info[1] < 0) return;  // too few words: the records are incomplete, the caller retries
+    const int e = blockIdx.x % plan.n_epochs;
+    const long long p = blockIdx.x / plan.n_epochs;
+    const long long pos = ehead[2 * (size_t)blockIdx.x];
+    const long long geo = ehead[2 * (size_t)blockIdx.x + 1];
+    const int S = (int)(geo & 0xffffffffll), n_act = (int)(geo >> 32);
+    const int tid = threadIdx.x;
+    if (tid >= n_act) return;
+    const int c = plan.e[e].c, i_hi = plan.e[e].i_hi;
+    const uint32_t M = plan.e[e].M;
+    const int Lb = rbase[(size_t)blockIdx.x * LT + tid];
+    if (Lb >= c) return;
+    unsigned long long m = rmask[(size_t)blockIdx.x * LT + tid];
+    const uint32_t* w = words + pos + (long long)tid * S;
+    int32_t* out = jout + p * (n - 1) + (n - 1 - i_hi) + Lb;
+    int room = c - Lb;  // accepts beyond the epoch's last step belong to nobody
+    while (m != 0ull && room > 0) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        *out++ = (int32_t)(w[k] & M);
+        --room;
     }
 }
 
@@ -748,8 +939,18 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
             MMX_CHECK_CUDA(cudaFuncSetAttribute(compose_scan16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)(SMEM_MAX - 1024)));
         }
-        emit_long_kernel<<<1, LT, smem_long, stream>>>(words, n_words, n, P, lp, reinterpret_cast<long long*>(info), jout);
+        unsigned long long* rmask = reinterpret_cast<unsigned long long*>(ws + pl.off_rm - 256);
+        uint16_t* rbase = reinterpret_cast<uint16_t*>(ws + pl.off_rb - 256);
+        long long* ehead = reinterpret_cast<long long*>(ws + pl.off_eh - 256);
+        MMX_REQUIRE(lp.n_epochs == pl.n_ep, "epoch plan mismatch");
+        emit_long_kernel<<<1, LT, smem_long, stream>>>(words, n_words, n, P, lp, reinterpret_cast<long long*>(info), jout,
+                                                       rmask, rbase, ehead);
         MMX_CHECK_CUDA(cudaGetLastError());
+        if (lp.n_epochs > 0) {
+            extract_long_kernel<<<(unsigned)((size_t)P * lp.n_epochs), LT, 0, stream>>>(
+                words, n, lp, reinterpret_cast<const long long*>(info), rmask, rbase, ehead, jout);
+            MMX_CHECK_CUDA(cudaGetLastError());
+        }
         const size_t nw = (size_t)(n + 2) / 2;
         const size_t smem_apply = ((nw + 3) & ~size_t(3)) * 4 + (pl.lists_in_smem ? (size_t)n * 2 : 0);
         uint16_t* glist = pl.lists_in_smem ? nullptr : reinterpret_cast<uint16_t*>(ws + pl.off_l - 256);

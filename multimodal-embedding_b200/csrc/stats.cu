@@ -164,17 +164,42 @@ boot_counts_kernel(const int32_t* __restrict__ list_t, int L, const int32_t* __r
 // stack merges it completes; every CTA builds that list once in shared memory (one thread, an explicit stack — a few
 // hundred leaves at most), so there is no limit on n. All leaves but the last have a multiple of 8 elements.
 //
-// gather_mean_kernel: one thread per resample row, 128 rows per CTA. The index rows are streamed through a 4-stage
-// cp.async ring of [128 rows x 32 columns] tiles (16-byte copies, 8 consecutive threads fetch 128 contiguous bytes
-// of one row; the 16-byte chunks of a row are XOR-swizzled so that every thread reads its own row with conflict-free
-// LDS.128), so the global traffic is fully coalesced although every thread walks its own row in numpy's order.
-constexpr int GR = 128;      // rows per CTA = threads
+// gather_mean_kernel: G threads per resample row, 128 / G rows per CTA. The G = 2^d subtrees at depth d of the
+// recursion are independent pairwise sums over consecutive column ranges; each thread walks ONE subtree in numpy's
+// order and the G partial sums are added pairwise in the recursion's own order (shuffles), which is numpy's result bit
+// for bit. More threads per row = more rows' worth of memory requests in flight: with one thread per row a
+// [3, 10 000, 1000] CI batch was 30 000 threads for 148 SMs. The index columns of the 128 (row, subtree) pairs of a CTA
+// are streamed through a 2-stage cp.async ring of [128 x 32] tiles (16-byte copies, 8 consecutive threads fetch 128
+// contiguous bytes; the 16-byte chunks of a tile row are XOR-swizzled so that every thread reads its own tile row with
+// conflict-free LDS.128), so the global traffic is fully coalesced although every thread walks its own column range.
+constexpr int GR = 128;      // (row, subtree) pairs per CTA = threads
 constexpr int GC = 32;       // columns per tile
-constexpr int GST = 4;       // tiles in flight
+constexpr int GST = 2;       // tiles in the ring (one in flight while one is consumed; 5 CTAs per SM)
+constexpr int GMAX = 32;     // subtrees per row at most (one warp adds them up)
 constexpr int DATA_SMEM_MAX = 96 * 1024;
 
-__device__ __forceinline__ int leaves_cap(int n) { return n / 56 + 2; }
-static inline int leaves_cap_host(long long n) { return (int)(n / 56 + 2); }
+// room for the leaf programs of the G subtrees of a vector of n: every subtree gets the same stride
+__host__ __device__ __forceinline__ int prog_stride(long long n, int lg) { return (int)(((n >> lg) + 8) / 56 + 3); }
+__host__ __device__ __forceinline__ int leaves_cap(long long n, int lg) { return prog_stride(n, lg) << lg; }
+
+// depth to which pairwise_sum(n) splits EVERY node (all nodes above that depth are longer than 128)
+static int full_split_depth(long long n) {
+    std::vector<long long> level{n};
+    int d = 0;
+    while (d < 5) {
+        std::vector<long long> next;
+        for (long long m : level) {
+            if (m <= 128) return d;
+            long long n2 = m / 2;
+            n2 -= n2 % 8;
+            next.push_back(n2);
+            next.push_back(m - n2);
+        }
+        level.swap(next);
+        ++d;
+    }
+    return d;
+}
 
 // leaves of pairwise_sum(n): size[l] (<= 128) and merges[l]; returns the count. One thread.
 __device__ int build_program(int n, uint8_t* size, uint8_t* merges) {
@@ -202,6 +227,33 @@ __device__ int build_program(int n, uint8_t* size, uint8_t* merges) {
     return nl;
 }
 
+// column range and leaf program of each of the G subtrees of pairwise_sum(n) at depth lg = log2(G): thread g walks
+// from the root to ITS subtree (bit k of g, from the top: right or left child) and flattens that subtree only, so the
+// set-up costs one short serial program per thread instead of one long one per CTA.
+struct SegPlan {
+    int start[GMAX], len[GMAX], prog[GMAX];   // first column, columns, offset of the program in psize / pmerge
+    int max_len;
+};
+__device__ void build_subtree(int n, int lg, int g, int stride, SegPlan* sp, uint8_t* psize, uint8_t* pmerge) {
+    int m = n, col = 0;
+    for (int k = lg - 1; k >= 0; --k) {
+        int n2 = m / 2;
+        n2 -= n2 % 8;
+        if ((g >> k) & 1) {
+            col += n2;
+            m -= n2;
+        } else {
+            m = n2;
+        }
+    }
+    sp->start[g] = col;
+    sp->len[g] = m;
+    sp->prog[g] = g * stride;
+    const int nl = build_program(m, psize + g * stride, pmerge + g * stride);
+    psize[g * stride + nl] = 0;                      // sentinel read after the subtree's last leaf
+    if (g == (1 << lg) - 1) sp->max_len = m;        // right halves are never shorter: the rightmost subtree is the longest
+}
+
 __device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
                  : "memory");
@@ -211,22 +263,34 @@ __device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
                  : "memory");
 }
 
-// sum of data[row[0 .. len)] in numpy's pairwise order; row = this CTA's first index row + seg_off
-template <bool DATA_SMEM>
+// sum of data[row[0 .. n)] in numpy's pairwise order for the CTA's rows; `rows` = the CTA's first index row + the
+// segment's first column. The result is valid in every thread of a row's group.
+// Every thread consumes only its own tile row, and a tile row is fetched by the thread itself and its lane neighbour
+// (the two request the two 16-byte halves of every 32-byte sector in the same instruction), so the ring needs no CTA
+// barrier: cp.async.wait_group + __syncwarp.
 __device__ double pairwise_rows(const double* __restrict__ data, const int32_t* __restrict__ rows, long long ld, int n_rows,
-                                int len, bool vec_ok, const uint8_t* psize, const uint8_t* pmerge, int32_t* tiles) {
+                                int lg, bool vec_ok, const SegPlan& sp, const uint8_t* psize, const uint8_t* pmerge,
+                                int32_t* tiles) {
     const int tid = threadIdx.x;
-    const int n_tiles = (len + GC - 1) / GC;
+    const int G = 1 << lg;
+    const int n_tiles = (sp.max_len + GC - 1) / GC;
+    // the two tile rows this thread helps to fetch: its own and its lane neighbour's
+    const int vrA = tid & ~1, vrB = tid | 1, odd = tid & 1;
+    const int lenA = (vrA >> lg) < n_rows ? sp.len[vrA & (G - 1)] : 0;
+    const int lenB = (vrB >> lg) < n_rows ? sp.len[vrB & (G - 1)] : 0;
+    const int32_t* srcA = rows + (long long)(vrA >> lg) * ld + sp.start[vrA & (G - 1)];
+    const int32_t* srcB = rows + (long long)(vrB >> lg) * ld + sp.start[vrB & (G - 1)];
     auto load_tile = [&](int t) {
         int32_t* dst = tiles + (size_t)(t % GST) * GR * GC;
         const int col0 = t * GC;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const int r = (tid >> 3) + 16 * k, ch = tid & 7;
+            const int vr = k < 4 ? vrA : vrB, len = k < 4 ? lenA : lenB;
+            const int ch = 2 * (k & 3) + odd;
             const int col = col0 + 4 * ch;
-            if (r < n_rows && col < len) {
-                const int32_t* src = rows + (long long)r * ld + col;
-                int32_t* d = dst + r * GC + ((ch ^ (r & 7)) << 2);
+            if (col < len) {
+                const int32_t* src = (k < 4 ? srcA : srcB) + col;
+                int32_t* d = dst + vr * GC + ((ch ^ (vr & 7)) << 2);
                 if (vec_ok && col + 4 <= len) {
                     cp_async_16(d, src);
                 } else {
@@ -240,18 +304,22 @@ __device__ double pairwise_rows(const double* __restrict__ data, const int32_t* 
         if (t < n_tiles) load_tile(t);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    const int my_g = tid & (G - 1);
+    const bool active = (tid >> lg) < n_rows;
+    const int len = active ? sp.len[my_g] : 0;
+    psize += sp.prog[my_g];
+    pmerge += sp.prog[my_g];
     double stack[32];
-    int sp = 0, li = 0;
+    int sptr = 0, li = 0;
     int full_left = psize[0] >> 3, tail = psize[0] & 7;
-    bool started = false;
-    double r0 = 0, r1 = 0, r2 = 0, r3 = 0, r4 = 0, r5 = 0, r6 = 0, r7 = 0, res = 0.0;
-    const bool active = tid < n_rows;
+    // -0.0 is the one start value that leaves every first addend unchanged, bit for bit (numpy starts from a[0..7])
+    double r0 = -0.0, r1 = -0.0, r2 = -0.0, r3 = -0.0, r4 = -0.0, r5 = -0.0, r6 = -0.0, r7 = -0.0, res = 0.0;
+    bool have_res = false;
     for (int t = 0; t < n_tiles; ++t) {
         asm volatile("cp.async.wait_group %0;" ::"n"(GST - 2) : "memory");
-        __syncthreads();  // tile t is visible, everybody is done with tile t - 1
+        __syncwarp();  // the neighbour's half of tile t has landed too; both lanes are done with tile t - 1
         if (t + GST - 1 < n_tiles) load_tile(t + GST - 1);
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (!active) continue;
         const int32_t* trow = tiles + (size_t)(t % GST) * GR * GC + tid * GC;
         const int col0 = t * GC;
 #pragma unroll
@@ -261,40 +329,42 @@ __device__ double pairwise_rows(const double* __restrict__ data, const int32_t* 
             const int4 ia = *reinterpret_cast<const int4*>(trow + (((2 * o) ^ (tid & 7)) << 2));
             const int4 ib = *reinterpret_cast<const int4*>(trow + (((2 * o + 1) ^ (tid & 7)) << 2));
             if (full_left > 0) {
-                const double a0 = data[ia.x], a1 = data[ia.y], a2 = data[ia.z], a3 = data[ia.w];
-                const double a4 = data[ib.x], a5 = data[ib.y], a6 = data[ib.z], a7 = data[ib.w];
-                if (!started) {
-                    r0 = a0; r1 = a1; r2 = a2; r3 = a3; r4 = a4; r5 = a5; r6 = a6; r7 = a7;
-                    started = true;
-                } else {
-                    r0 += a0; r1 += a1; r2 += a2; r3 += a3; r4 += a4; r5 += a5; r6 += a6; r7 += a7;
-                }
+                r0 += data[ia.x]; r1 += data[ia.y]; r2 += data[ia.z]; r3 += data[ia.w];
+                r4 += data[ib.x]; r5 += data[ib.y]; r6 += data[ib.z]; r7 += data[ib.w];
                 if (--full_left > 0) continue;
                 res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+                r0 = r1 = r2 = r3 = r4 = r5 = r6 = r7 = -0.0;
+                have_res = true;
                 if (tail > 0) continue;  // the leftovers of the last leaf follow in the next octet
             } else {
                 // fewer than 8 elements: a leaf shorter than 8 (sequential from 0.0) or the leftovers of the last leaf
                 const int idx8[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
-                if (!started) res = 0.0;
+                if (!have_res) res = 0.0;
 #pragma unroll
                 for (int e = 0; e < 8; ++e)
                     if (e < tail) res += data[idx8[e]];
             }
             // ---- the leaf is complete: push, merge, next leaf
-            stack[sp++] = res;
+            stack[sptr++] = res;
             for (int m = pmerge[li]; m > 0; --m) {
-                --sp;
-                stack[sp - 1] = stack[sp - 1] + stack[sp];
+                --sptr;
+                stack[sptr - 1] = stack[sptr - 1] + stack[sptr];
             }
             ++li;
             full_left = psize[li] >> 3;   // one sentinel entry follows the last leaf
             tail = psize[li] & 7;
-            started = false;
+            have_res = false;
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();  // the ring is free for the next segment
-    return active ? stack[0] : 0.0;
+    __syncwarp();  // the lane pair's ring rows are free for the next segment
+    // ---- the G subtree sums of a row are added in the recursion's order: neighbours first
+    double s = active ? stack[0] : 0.0;
+    for (int o = 1; o < G; o <<= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, s, o);
+        s = s + other;        // only the left member of each pair is used further up (and IEEE addition commutes)
+    }
+    return s;
 }
 
 // out[r] = mean(data[idx[r, 0:n1]])                       (n2 == 0, K4)
@@ -302,11 +372,13 @@ __device__ double pairwise_rows(const double* __restrict__ data, const int32_t* 
 template <bool DATA_SMEM>
 __global__ void __launch_bounds__(GR)
 gather_mean_kernel(const double* __restrict__ data, int n_data, const int32_t* __restrict__ idx, long long ld, int R,
-                   int n1, int n2, int vec1, int vec2, double* __restrict__ out) {
+                   int n1, int n2, int lg, int vec1, int vec2, double* __restrict__ out) {
     extern __shared__ __align__(16) uint8_t gsm[];
+    __shared__ SegPlan sp1, sp2;
     int32_t* tiles = reinterpret_cast<int32_t*>(gsm);                            // [GST][GR][GC]
     uint8_t* prog = gsm + (size_t)GST * GR * GC * 4;
-    const int cap1 = leaves_cap(n1), cap2 = n2 > 0 ? leaves_cap(n2) : 0;
+    const int cap1 = leaves_cap(n1, lg), cap2 = n2 > 0 ? leaves_cap(n2, lg) : 0;
+    const int stride1 = prog_stride(n1, lg), stride2 = prog_stride(n2, lg);
     uint8_t* ps1 = prog;
     uint8_t* pm1 = ps1 + cap1;
     uint8_t* ps2 = pm1 + cap1;
@@ -316,30 +388,30 @@ gather_mean_kernel(const double* __restrict__ data, int n_data, const int32_t* _
     data += (long long)blockIdx.y * n_data;
     idx += (long long)blockIdx.y * R * ld;
     out += (long long)blockIdx.y * R;
-    if (threadIdx.x == 0) {
-        const int l1 = build_program(n1, ps1, pm1);
-        ps1[l1] = 0;                                  // sentinel read after the last leaf
-        if (n2 > 0) {
-            const int l2 = build_program(n2, ps2, pm2);
-            ps2[l2] = 0;
-        }
-    }
+    const int G = 1 << lg;
+    if ((int)threadIdx.x < G) build_subtree(n1, lg, threadIdx.x, stride1, &sp1, ps1, pm1);
+    if (n2 > 0 && (int)threadIdx.x >= 32 && (int)threadIdx.x < 32 + G)
+        build_subtree(n2, lg, threadIdx.x - 32, stride2, &sp2, ps2, pm2);
     const double* d = data;
     if (DATA_SMEM) {
         for (int i = threadIdx.x; i < n_data; i += GR) sm_data[i] = data[i];
         d = sm_data;
     }
     __syncthreads();
-    const int row0 = blockIdx.x * GR;
-    const int n_rows = min(GR, R - row0);
-    const int32_t* rows = idx + (long long)row0 * ld;
-    const double s1 = pairwise_rows<DATA_SMEM>(d, rows, ld, n_rows, n1, vec1 != 0, ps1, pm1, tiles);
-    double res = s1 / (double)n1;
-    if (n2 > 0) {
-        const double s2 = pairwise_rows<DATA_SMEM>(d, rows + n1, ld, n_rows, n2, vec2 != 0, ps2, pm2, tiles);
-        res = fabs(res - s2 / (double)n2);
+    // persistent over row blocks: the programs and the data vector are set up once per CTA
+    const int rows_per_cta = GR >> lg;
+    const int r = threadIdx.x >> lg;
+    for (int row0 = blockIdx.x * rows_per_cta; row0 < R; row0 += gridDim.x * rows_per_cta) {
+        const int n_rows = min(rows_per_cta, R - row0);
+        const int32_t* rows = idx + (long long)row0 * ld;
+        const double s1 = pairwise_rows(d, rows, ld, n_rows, lg, vec1 != 0, sp1, ps1, pm1, tiles);
+        double res = s1 / (double)n1;
+        if (n2 > 0) {
+            const double s2 = pairwise_rows(d, rows + n1, ld, n_rows, lg, vec2 != 0, sp2, ps2, pm2, tiles);
+            res = fabs(res - s2 / (double)n2);
+        }
+        if ((threadIdx.x & (G - 1)) == 0 && r < n_rows) out[row0 + r] = res;
     }
-    if ((int)threadIdx.x < n_rows) out[row0 + threadIdx.x] = res;
 }
 
 }  // namespace stats
@@ -427,12 +499,16 @@ static int launch_gather_mean(const double* data, int n_data, const int32_t* idx
     MMX_REQUIRE(n1 >= 1 && n2 >= 0 && ld >= (int64_t)n1 + n2, "bad segment sizes");
     MMX_REQUIRE(batch >= 1 && batch <= 65535, "batch out of range");
     if (R == 0) return 0;
-    const size_t prog = 2 * (size_t)(leaves_cap_host(n1) + (n2 > 0 ? leaves_cap_host(n2) : 0));
+    // threads per row: as many subtrees as the recursion offers (both segments), until ~64 warps per SM are in flight
+    int lg = full_split_depth(n1);
+    if (n2 > 0) lg = std::min(lg, full_split_depth(n2));
+    while (lg > 0 && ((long long)R * batch << (lg - 1)) >= (long long)sm_count() * 2048) --lg;
+    const size_t prog = 2 * (size_t)(leaves_cap(n1, lg) + (n2 > 0 ? leaves_cap(n2, lg) : 0));
     const size_t base = (((size_t)GST * GR * GC * 4 + prog + 15) & ~size_t(15));
     MMX_REQUIRE(base <= 200 * 1024, "vectors too long for the pairwise-sum program (n1=%d n2=%d)", n1, n2);
     const bool in_smem = (size_t)n_data * 8 <= (size_t)DATA_SMEM_MAX && base + (size_t)n_data * 8 <= 200 * 1024;
     const size_t smem = base + (in_smem ? (size_t)n_data * 8 : 0);
-    // 16-byte copies need every row segment to start on a 16-byte boundary
+    // 16-byte copies need every column range to start on a 16-byte boundary (subtree boundaries are multiples of 8)
     const bool al = (reinterpret_cast<uintptr_t>(idx) % 16 == 0) && (ld % 4 == 0) && ((int64_t)R * ld % 4 == 0);
     const int vec1 = al ? 1 : 0, vec2 = (al && n1 % 4 == 0) ? 1 : 0;
     static const char gather_tag = 0;
@@ -440,11 +516,14 @@ static int launch_gather_mean(const double* data, int n_data, const int32_t* idx
         MMX_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         MMX_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
-    const dim3 grid((R + GR - 1) / GR, batch);
+    const int rows_per_cta = GR >> lg;
+    const int row_blocks = (R + rows_per_cta - 1) / rows_per_cta;
+    const int ctas_per_sm = std::max(1, (int)((220 * 1024) / (smem + 1024)));
+    const dim3 grid(std::min(row_blocks, std::max(1, sm_count() * ctas_per_sm / batch)), batch);
     if (in_smem)
-        gather_mean_kernel<true><<<grid, GR, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, vec1, vec2, out);
+        gather_mean_kernel<true><<<grid, GR, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, lg, vec1, vec2, out);
     else
-        gather_mean_kernel<false><<<grid, GR, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, vec1, vec2, out);
+        gather_mean_kernel<false><<<grid, GR, smem, stream>>>(data, n_data, idx, ld, R, n1, n2, lg, vec1, vec2, out);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
