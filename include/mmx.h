@@ -137,6 +137,15 @@ int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_above, cons
                     int64_t words_per_row, const int32_t* col2unit, const int32_t* q_unit, const uint8_t* mult, int B,
                     int64_t n_units, int64_t nq, int32_t* correct, int32_t* q_hits1, cudaStream_t stream);
 
+/* Shard merge of the above-GT bitmask (the counts and bit columns of main.py:331-378's rank tests are additive /
+ * concatenable over gallery shards). gathered uint32 [n_shards, nq, wmax] = every shard's bit columns as ONE all-gather
+ * delivers them (bit j of word w of shard s = global column shard_begin_h[s] + 32 w + j; bits beyond a shard's width are
+ * ignored); shard_begin_h = HOST array of n_shards + 1 global column offsets (<= 64 shards). Writes the merged bitmask
+ * above_bits [nq, words_per_row] (a shard may start inside a 32-column word) and cnt_above [nq] (nullable) = the popcount
+ * of every merged row, i.e. the summed strict-greater counts — no second collective. */
+int mmx_place_bit_columns(const uint32_t* gathered, int n_shards, int64_t nq, int64_t wmax, const int64_t* shard_begin_h,
+                          uint32_t* above_bits, int64_t words_per_row, int32_t* cnt_above, cudaStream_t stream);
+
 /* LIST mode — K1 + K3 for galleries whose [nq, ng] above-GT bitmask does not fit in memory (10^6 x 10^6
  * would be 125 GB of bits). Same identity as above; the above-GT set of a query is kept as a list of at most `cap`
  * columns, which is all K3 ever reads for queries with cnt_above <= cap and enough for min(c_q, 10) otherwise

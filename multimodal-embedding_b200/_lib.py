@@ -16,7 +16,8 @@ from typing import Optional
 _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 LIB_PATH = CSRC / "libmmx.so"
-SOURCES = ["mmx_host.cu", "maxsim.cu", "dense_rank.cu", "rank_scores.cu", "topk.cu", "stats.cu", "rng.cu", "shuffle.cu"]
+SOURCES = ["mmx_host.cu", "maxsim.cu", "dense_rank.cu", "rank_scores.cu", "topk.cu", "stats.cu", "rng.cu", "shuffle.cu",
+           "bits.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -157,6 +158,10 @@ _SIGNATURES = {
     "mmx_perm_shuffle": (_c.c_int, [
         _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,    # words, n_words, n, P, perm, info
         _c.c_void_p, _c.c_size_t, _c.c_void_p,                                    # workspace, bytes, stream
+    ]),
+    "mmx_place_bit_columns": (_c.c_int, [
+        _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p,               # gathered, n_shards, nq, wmax, shard_begin_h
+        _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p,                        # above_bits, words_per_row, cnt_above, stream
     ]),
     "mmx_perm_stats": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,  # combined,n1,n2,perm,P,diffs,stream

@@ -574,7 +574,7 @@ H2D_DOC_CHUNKS = 8   # host-resident documents are uploaded in this many pieces,
 
 
 def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device,
-                     flags: Optional[np.ndarray] = None, keep: Optional[dict] = None) -> torch.Tensor:
+                     flags: Optional[np.ndarray] = None, keep: Optional[dict] = None, group=None) -> torch.Tensor:
     """K2 over documents that still live in host memory: the upload of document chunk c+1 (copy stream, pinned
     source) overlaps the scoring of chunk c, so PCIe time hides behind the tensor cores. Returns fp32 [nq, nd].
     `flags`: the documents' zero-padding flags when they are not those of this list taken alone (a shard).
@@ -582,7 +582,16 @@ def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device
     nq, nd = len(qv), len(dv)
     if flags is None:
         flags = _pad_flags(dv.lens)                   # chunk-of-10 padding flags of the WHOLE list (main.py:465)
-    q_flat, q_off = qv.to_device(dev)
+    if group is not None and not qv.flat.is_cuda:
+        # replicated queries: every rank uploads 1/N of them, one all-gather over NVLink spreads the slices
+        from . import sharded
+        src_q = _as_bf16(qv.flat, "multi-vector embeddings")
+        q_flat = sharded.gather_rows(src_q if src_q.is_pinned() else src_q.pin_memory(), dev, group)
+        off = np.zeros(len(qv.lens) + 1, dtype=np.int32)
+        off[1:] = np.cumsum(qv.lens)
+        q_off = _np_h2d(off, dev, torch.int32)
+    else:
+        q_flat, q_off = qv.to_device(dev)
     n_chunks = 1 if dv.flat.is_cuda else max(1, min(H2D_DOC_CHUNKS, nd // 64))
     if n_chunks == 1:
         d_flat, d_off = dv.to_device(dev)
@@ -628,7 +637,8 @@ BITMASK_LIMIT_BYTES = 16 << 30     # above-GT bitmasks larger than this switch t
 
 def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: Dict, n_iterations: int, rng=None,
                             group=None, timings: Optional[Dict[str, float]] = None, list_mode: Optional[bool] = None,
-                            list_cap: Optional[int] = None) -> Optional[Dict[str, Any]]:
+                            list_cap: Optional[int] = None, shard_sizes: Optional[Sequence[int]] = None,
+                            keep: Optional[dict] = None) -> Optional[Dict[str, Any]]:
     """One retrieval protocol (T2I-style: every query has one ground-truth document) scored, ranked, bootstrapped and
     aggregated like main.py:586-651 — for the configurations whose query set is not "caption 0 of every image"
     (BASELINE.json configs 4-5: 25 000 caption queries against 5 000 / 100 000 documents).
@@ -636,8 +646,14 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     queries / docs: bf16 tensors [n, d] (dense) or FlatMultiVector / lists of [L_i, 128] (ColPali). The bootstrap unit
     is the document: an iteration draws ``choice(n_docs, n_docs)`` documents, each draw brings along its queries.
     With a torch.distributed ``group`` (world > 1) every rank passes ITS contiguous shard of the documents
-    (``sharded.shard_bounds``) and all queries; rank 0 returns the result, the others None.
-    numpy stream: n_iterations x choice(n_docs, n_docs), then 3 x 10 000 x choice(values, n_iterations).
+    (``sharded.shard_bounds``) and all queries; rank 0 returns the result, the others None. ``shard_sizes`` (documents
+    per rank, known to callers that made the shards) saves the collective that otherwise asks for them.
+    numpy stream: n_iterations x choice(n_docs, n_docs), then 3 x 10 000 x choice(values, n_iterations) — rank 0's
+    generator; its state is broadcast so that every rank can take its share of the statistics.
+    Collectives per call (world > 1): [sizes], [ColPali: document lengths], generator state (2.5 KB), queries
+    (host-resident: 1/N uploaded per rank, all-gathered over NVLink), thresholds all-reduce(MAX), ONE all-gather of the
+    bit columns, and two small all-gathers that reassemble the bootstrap counts / CI means computed in blocks.
+    ``keep`` (dict) receives the merged rank structures (``ranks``) for callers that go on (per-query vectors).
 
     Dense galleries whose [n_queries, n_docs] above-GT bitmask would exceed BITMASK_LIMIT_BYTES (a 10^6 x 10^6 problem
     needs 125 GB of bits) run in LIST mode (``list_mode`` forces it either way): K1 keeps at most
@@ -649,6 +665,8 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     marks = [("enter", time.perf_counter())]
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
+    if world > 1 and group is None:
+        group = dist.group.WORLD
     q2d = np.asarray(query_to_doc, dtype=np.int32)
     nq = len(q2d)
     colpali = m_info["type"] == "colpali"
@@ -658,35 +676,53 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         n_local = len(dv)
     else:
         n_local = docs.shape[0]
+    if world > 1 and shard_sizes is None:
+        sizes = torch.zeros((world, 1), dtype=torch.int64, device=dev)
+        dist.all_gather(list(sizes.unbind(0)), torch.tensor([n_local], dtype=torch.int64, device=dev), group=group)
+        shard_sizes = sizes.view(-1).tolist()                            # one device->host read
     if world > 1:
-        sizes = torch.tensor([n_local], device=dev)
-        allsz = [torch.zeros_like(sizes) for _ in range(world)]
-        dist.all_gather(allsz, sizes, group=group)
-        ends = np.cumsum([int(s.item()) for s in allsz])
-        bounds = [(int(e - int(s.item())), int(e)) for e, s in zip(ends, allsz)]
+        ends = np.cumsum(np.asarray(shard_sizes, dtype=np.int64))
+        bounds = [(int(e - sz), int(e)) for e, sz in zip(ends, shard_sizes)]
+        if bounds[rank][1] - bounds[rank][0] != n_local:
+            raise ValueError("shard_sizes does not match this rank's documents")
     else:
         bounds = [(0, n_local)]
     g_base, n_docs = bounds[rank][0], bounds[-1][1]
     shard_flags = None
     if colpali and world > 1:
         # the reference pads inside chunks of 10 consecutive documents of the WHOLE list (main.py:465): a shard that
-        # does not start on a multiple of 10 needs its neighbours' lengths to know which of its documents get a zero row
-        all_lens: List[Any] = [None] * world
-        dist.all_gather_object(all_lens, np.asarray(dv.lens, dtype=np.int64), group=group)
-        shard_flags = _pad_flags(np.concatenate(all_lens))[g_base:g_base + n_local]
-    # ---- the reference's numpy stream (the draws do not depend on the scores). Device mode (K6): one small CTA on a
-    # side stream regenerates MT19937 while the embeddings cross PCIe and the scoring kernel runs.
+        # does not start on a multiple of 10 needs its neighbours' lengths to know which of its documents get a zero
+        # row. One fixed-size all-gather of the (padded) length vectors, one device->host read.
+        n_max = max(e - b_ for b_, e in bounds)
+        mine = torch.zeros(n_max, dtype=torch.int32)
+        mine[:n_local] = torch.from_numpy(np.asarray(dv.lens, dtype=np.int32))
+        all_l = torch.empty((world, n_max), dtype=torch.int32, device=dev)
+        dist.all_gather(list(all_l.unbind(0)), mine.to(dev), group=group)
+        all_h = all_l.cpu().numpy()
+        lens_all = np.concatenate([all_h[r, : e - b_] for r, (b_, e) in enumerate(bounds)])
+        shard_flags = _pad_flags(lens_all)[g_base:g_base + n_local]
+    # ---- the reference's numpy stream (the draws do not depend on the scores). K6p on a side stream regenerates it
+    # while the embeddings cross PCIe and the scoring kernel runs — on EVERY rank (the same 2.5 KB state, broadcast
+    # from rank 0), so that each can bootstrap its own block of iterations afterwards.
     r = _rng(rng)
-    if rank == 0 and DEVICE_RNG:
-        side = _aux_stream(dev, "rng")
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+    if list_mode is None:
+        list_mode = (not colpali) and nq * n_docs // 8 > BITMASK_LIMIT_BYTES
+    if list_mode and colpali:
+        raise ValueError("LIST mode applies to the dense path (the MaxSim path materialises its score matrix)")
+    split_stats = world > 1 and DEVICE_RNG and not list_mode   # LIST mode's recount round trips stay on rank 0
+    if rank == 0 or split_stats:
+        if DEVICE_RNG:
             drng = ops.DeviceRng(r, dev)
-            sample_indices = drng.randint(n_docs, n_iterations * n_docs).view(n_iterations, n_docs)  # main.py:588
-            ci_idx = drng.randint(n_iterations, len(KS) * N_BOOTSTRAP * n_iterations).view(
-                len(KS), N_BOOTSTRAP, n_iterations)                       # main.py:269, the three CIs' draws in stream order
-            rng_done = torch.cuda.Event()
-            rng_done.record(side)
+            if split_stats:
+                dist.broadcast(drng.state, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            side = _aux_stream(dev, "rng")
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                sample_indices = drng.randint(n_docs, n_iterations * n_docs).view(n_iterations, n_docs)  # main.py:588
+                ci_idx = drng.randint(n_iterations, len(KS) * N_BOOTSTRAP * n_iterations).view(
+                    len(KS), N_BOOTSTRAP, n_iterations)                   # main.py:269, the three CIs' draws in stream order
+                rng_done = torch.cuda.Event()
+                rng_done.record(side)
     marks.append(("rng_queued", time.perf_counter()))
     gt_off = torch.arange(nq + 1, dtype=torch.int32, device=dev)
     gt_idx = _np_h2d(q2d, dev, torch.int32)
@@ -694,11 +730,12 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     # ---- score + threshold pass on this rank's shard (async)
     if colpali:
         ev[0].record()
-        S = _maxsim_streamed(qv, dv, dev, shard_flags)
+        S = _maxsim_streamed(qv, dv, dev, shard_flags, group=group if world > 1 else None)
         ev[1].record()
         local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, threshold_only=True)
     else:
-        Q, G = _h2d(_as_bf16(queries, "queries"), dev), _h2d(_as_bf16(docs, "docs"), dev)
+        Q = queries if queries.is_cuda else sharded.gather_rows(_as_bf16(queries, "queries"), dev, group if world > 1 else None)
+        Q, G = _as_bf16(Q, "queries"), _h2d(_as_bf16(docs, "docs"), dev)
         ev[0].record()
         local = ops.dense_rank(Q, G, gt_off, gt_idx, g_base=g_base, threshold_only=True)
         ev[1].record()
@@ -710,10 +747,6 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
                          torch.int32)
     marks.append(("score_queued", time.perf_counter()))
     thr = sharded.merge_thresholds(local.thr, group)
-    if list_mode is None:
-        list_mode = (not colpali) and nq * n_docs // 8 > BITMASK_LIMIT_BYTES
-    if list_mode and colpali:
-        raise ValueError("LIST mode applies to the dense path (the MaxSim path materialises its score matrix)")
     if colpali:
         local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, thr=thr)
     elif list_mode:
@@ -722,29 +755,40 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     else:
         local = ops.dense_rank(Q, G, gt_off, gt_idx, g_base=g_base, thr=thr)
     ranks = sharded.merge_ranks(local, bounds, group)
-    if rank != 0:
-        if list_mode:
-            sharded.unlisted_round(recount, None, None, group)               # serve rank 0's recount, if there is one
-        return None
     ranks.q_unit = gt_idx
-    if DEVICE_RNG:
-        torch.cuda.current_stream().wait_event(rng_done)
-    mult = ops.bincount(sample_indices, n_docs)
-    if list_mode:
-        rounds, k3_stats = [], {}
+    if keep is not None:
+        keep["ranks"] = ranks
+    if not split_stats:
+        # one GPU, LIST mode (exact-recount round trips) and the host-RNG mode keep the statistics on rank 0
+        if rank != 0:
+            if list_mode:
+                sharded.unlisted_round(recount, None, None, group)           # serve rank 0's recount, if there is one
+            return None
+        if DEVICE_RNG:
+            torch.cuda.current_stream().wait_event(rng_done)
+        mult = ops.bincount(sample_indices, n_docs)
+        if list_mode:
+            rounds, k3_stats = [], {}
 
-        def resolve(pairs, mult_rows):
-            rounds.append(1)
-            return sharded.unlisted_round(recount, pairs, mult_rows, group)
-        correct = ops.boot_counts_lists(ranks, mult, resolve, stats=k3_stats)                    # [B, 3] int32
-        if not rounds:
-            sharded.unlisted_round(recount, None, None, group)               # nothing unsettled: release the other ranks
+            def resolve(pairs, mult_rows):
+                rounds.append(1)
+                return sharded.unlisted_round(recount, pairs, mult_rows, group)
+            correct = ops.boot_counts_lists(ranks, mult, resolve, stats=k3_stats)                    # [B, 3] int32
+            if not rounds:
+                sharded.unlisted_round(recount, None, None, group)           # nothing unsettled: release the other ranks
+        else:
+            correct = ops.boot_counts(ranks, mult)                                                   # [B, 3] int32
+        # query copies drawn in each iteration (integer sum: the same doubles as summing float64 copies)
+        denom = mult[:, gt_idx.long()].sum(dim=1, dtype=torch.int64).to(torch.float64)
+        values = 100.0 * correct.to(torch.float64) / denom[:, None]                                  # main.py:358
+        means = ops.ci_means_batched(values.t().contiguous(), ci_idx)                                # three CIs, one launch
     else:
-        correct = ops.boot_counts(ranks, mult)                                                   # [B, 3] int32
-    # query copies drawn in each iteration (integer sum: the same doubles as summing float64 copies)
-    denom = mult[:, gt_idx.long()].sum(dim=1, dtype=torch.int64).to(torch.float64)
-    values = 100.0 * correct.to(torch.float64) / denom[:, None]                                  # main.py:358
-    means = ops.ci_means_batched(values.t().contiguous(), ci_idx)                                # three CIs, one launch
+        torch.cuda.current_stream().wait_event(rng_done)
+        for t in (sample_indices, ci_idx):
+            t.record_stream(torch.cuda.current_stream())
+        values, means = sharded.bootstrap_stats(ranks, sample_indices, ci_idx, gt_idx, n_docs, group)
+        if rank != 0:
+            return None
     marks.append(("stats_queued", time.perf_counter()))
     if DEVICE_RNG:
         drng.commit()                                                    # numpy's generator ends where the reference's would

@@ -360,6 +360,23 @@ def merge_topk(gathered_s: torch.Tensor, gathered_i: torch.Tensor, k: int) -> Tu
     return top_s, top_i
 
 
+def place_bit_columns(gathered: torch.Tensor, bounds: Sequence[Tuple[int, int]]) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Shard merge: gathered int32 CUDA [n_shards, nq, wmax] bit columns of every shard (what one
+    all-gather delivers) + the shards' global [begin, end) column ranges -> (bits int32 [nq, ceil(n_cols / 32)],
+    cnt_above int32 [nq] = popcount of every merged row). One kernel; a shard may start inside a 32-column word."""
+    _need_cuda(gathered)
+    gathered = gathered.contiguous()
+    n_shards, nq, wmax = gathered.shape
+    begin = np.array([b for b, _ in bounds] + [bounds[-1][1]], dtype=np.int64)
+    n_cols = int(begin[-1])
+    wpr = (n_cols + 31) // 32
+    bits = torch.empty((nq, wpr), dtype=torch.int32, device=gathered.device)
+    cnt = torch.empty((nq,), dtype=torch.int32, device=gathered.device)
+    _lib.check(_lib.lib().mmx_place_bit_columns(gathered.data_ptr(), n_shards, nq, wmax, begin.ctypes.data,
+                                                bits.data_ptr(), wpr, cnt.data_ptr(), _stream()))
+    return bits, cnt
+
+
 def bincount(sample_idx: torch.Tensor, n_units: int) -> torch.Tensor:
     """int32 CUDA [B, n_draws] -> uint8 CUDA [B, n_units] multiplicities (saturated at 255)."""
     _need_cuda(sample_idx)

@@ -1,9 +1,10 @@
 """Gallery/document sharding across the GPUs of one box: one process per GPU, queries replicated,
-gallery columns split into contiguous balanced shards, exactly two tiny collectives per scoring pass:
+gallery columns split into contiguous balanced shards, exactly two collectives per scoring pass:
 
-  1. all-reduce(MAX) of the per-query GT thresholds (the GT column of a query lives on one shard only);
-  2. all-reduce(SUM) of the strict-greater counts + all-gather of each shard's bitmask columns (or, in LIST mode for
-     galleries whose bitmask does not fit, of each shard's truncated above-GT column list).
+  1. all-reduce(MAX) of the per-query GT thresholds (4 bytes per query; the GT column lives on one shard only) — the tiny
+     pre-pass of SURVEY 8e(i);
+  2. ONE all-gather of each shard's bitmask columns (or, in LIST mode for galleries whose bitmask does not fit, of each
+     shard's truncated above-GT column list); the counts are the popcounts of the merged rows, no second reduction.
 When the retrieved items themselves are wanted, ONE all-gather of a fixed-size record per query — the shard's top-k
 scores and global column ids, 8k bytes — followed by a local merge (mmx_merge_topk) gives the global top-k.
 
@@ -48,21 +49,32 @@ def merge_thresholds(thr: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def merge_ranks(local: ProtocolRanks, bounds: List[Tuple[int, int]], group=None) -> ProtocolRanks:
-    """Sum the counts, concatenate the bit columns of all shards (same result on every rank)."""
+    """ONE all-gather per scoring pass: every shard's bit columns travel once, each rank then shifts them to
+    their global bit offsets, ORs them together and takes the merged rows' popcounts as the counts (mmx_place_bit_columns;
+    the same result on every rank). Without bit columns (want_bits=False) the counts are all-reduced instead; in LIST mode
+    the record is the shard's column list."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
-    cnt = local.cnt_above.clone()
-    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-    bits = None
+    cnt, bits = None, None
     if local.bits is not None:
         nq = local.bits.shape[0]
         wmax = max((e - b + 31) // 32 for b, e in bounds)
-        mine = torch.zeros((nq, wmax), dtype=local.bits.dtype, device=local.bits.device)
-        mine[:, : local.bits.shape[1]] = local.bits
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine, group=group)
-        bits = place_bit_columns(parts, bounds)
+        gathered = torch.empty((world, nq, wmax), dtype=local.bits.dtype, device=local.bits.device)
+        mine = local.bits
+        if mine.shape[1] != wmax:
+            mine = torch.zeros((nq, wmax), dtype=local.bits.dtype, device=local.bits.device)
+            mine[:, : local.bits.shape[1]] = local.bits
+        dist.all_gather(list(gathered.unbind(0)), mine.contiguous(), group=group)
+        if gathered.is_cuda:
+            from . import ops
+            bits, cnt = ops.place_bit_columns(gathered, bounds)
+        else:                                            # gloo host-logic tests: the same merge in torch
+            bits = place_bit_columns(list(gathered.unbind(0)), bounds)
+            cnt = _popcount_rows(bits)
+    else:
+        cnt = local.cnt_above.clone()
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     list_i = list_n = None
     if local.list_i is not None:
         # LIST mode: ONE all-gather of a fixed-size record per query — the shard's `cap` column ids and its cursor
@@ -74,6 +86,13 @@ def merge_ranks(local: ProtocolRanks, bounds: List[Tuple[int, int]], group=None)
         list_n = torch.stack([p[:, cap] for p in parts]).contiguous()
     return ProtocolRanks(thr=local.thr, cnt_above=cnt, bits=bits, n_cols=bounds[-1][1], col2unit=local.col2unit,
                          q_unit=local.q_unit, list_i=list_i, list_n=list_n)
+
+
+def _popcount_rows(bits: torch.Tensor) -> torch.Tensor:
+    """Row popcounts of an int32 bitmask on the CPU (host-logic tests only; the GPU path counts inside the merge kernel)."""
+    import numpy as np
+    u8 = bits.contiguous().numpy().view(np.uint8)
+    return torch.from_numpy(np.unpackbits(u8, axis=1).sum(axis=1).astype(np.int32))
 
 
 def unlisted_round(local_resolve, pairs, mult_rows, group=None) -> torch.Tensor:
@@ -126,6 +145,65 @@ def place_bit_columns(parts: List[torch.Tensor], bounds: List[Tuple[int, int]]) 
     out = out[:, : (n_cols + 31) // 32]
     out = torch.where(out >= (1 << 31), out - (1 << 32), out)          # back to the int32 bit pattern
     return out.to(parts[0].dtype).contiguous()
+
+
+def gather_rows(host_rows: torch.Tensor, dev: torch.device, group=None) -> torch.Tensor:
+    """A replicated host matrix onto every GPU at NVLink cost: rank r uploads rows [r n / N, (r + 1) n / N) over its own
+    PCIe link and ONE all-gather spreads the slices (the 128 MB query matrix of configs[3] crossed PCIe eight times when
+    every rank uploaded all of it)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1 or host_rows.is_cuda:
+        return host_rows.to(dev, non_blocking=True)
+    rank = dist.get_rank(group)
+    n = host_rows.shape[0]
+    per = -(-n // world)
+    out = torch.empty((world * per,) + tuple(host_rows.shape[1:]), dtype=host_rows.dtype, device=dev)
+    a, b = min(n, rank * per), min(n, (rank + 1) * per)
+    mine = out[rank * per: rank * per + per]
+    if b > a:
+        mine[: b - a].copy_(host_rows[a:b], non_blocking=True)
+    dist.all_gather(list(out.view(world, per, *host_rows.shape[1:]).unbind(0)), mine, group=group)
+    return out[:n]
+
+
+def bootstrap_stats(ranks: ProtocolRanks, sample_indices: torch.Tensor, ci_idx: torch.Tensor, q_unit: torch.Tensor,
+                    n_units: int, group=None, boot_fn=None):
+    """The statistics tail of a sharded pass — K3 over the bootstrap iterations, K4 over the CI resample rows — split
+    over the ranks instead of serialised on rank 0: every rank holds the merged rank structures and the same numpy
+    stream (sample_indices int32 [B, n_units], ci_idx int32 [M, R, B]), takes its block of iterations / resample rows,
+    and two small all-gathers put the pieces together. Returns (values fp64 [B, M], means fp64 [M, R]) on every rank,
+    bit-identical to the single-GPU tail (integer counts; the means are computed row by row either way).
+    boot_fn(ranks, mult) -> int32 [b, M] defaults to ops.boot_counts."""
+    from . import ops
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    boot_fn = boot_fn or ops.boot_counts
+    B = sample_indices.shape[0]
+    per = -(-B // world)
+    b0, b1 = min(B, rank * per), min(B, (rank + 1) * per)
+    dev = sample_indices.device
+    rec = torch.zeros((per, 4), dtype=torch.int64, device=dev)       # correct@1/5/10 + query copies drawn
+    if b1 > b0:
+        mult = ops.bincount(sample_indices[b0:b1].contiguous(), n_units)
+        rec[: b1 - b0, :3] = boot_fn(ranks, mult)
+        rec[: b1 - b0, 3] = mult[:, q_unit.long()].sum(dim=1, dtype=torch.int64)
+    if world > 1:
+        allrec = torch.empty((world, per, 4), dtype=torch.int64, device=dev)
+        dist.all_gather(list(allrec.unbind(0)), rec, group=group)
+        rec = allrec.view(world * per, 4)
+    rec = rec[:B]
+    values = 100.0 * rec[:, :3].to(torch.float64) / rec[:, 3:4].to(torch.float64)         # main.py:358, IEEE division
+    M, R, _ = ci_idx.shape
+    perr = -(-R // world)
+    r0, r1 = min(R, rank * perr), min(R, (rank + 1) * perr)
+    means = torch.zeros((M, perr), dtype=torch.float64, device=dev)
+    if r1 > r0:
+        means[:, : r1 - r0] = ops.ci_means_batched(values.t().contiguous(), ci_idx[:, r0:r1].contiguous())
+    if world > 1:
+        allm = torch.empty((world, M, perr), dtype=torch.float64, device=dev)
+        dist.all_gather(list(allm.unbind(0)), means, group=group)
+        means = allm.permute(1, 0, 2).reshape(M, world * perr)
+    return values, means[:, :R].contiguous()
 
 
 def merge_topk(top_s: torch.Tensor, top_i: torch.Tensor, group=None, merge_fn=None):
