@@ -496,7 +496,8 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
         caps = t2i_captions if t2i_captions is not None else [""] * n_images
         caption_table = None
     aggregated["_failure_analysis"] = aggregate_failure_from_hits(                                      # main.py:664
-        caps, hits, drawn, first_seen_order=_first_seen_order(sample_indices, n_images), table=caption_table)
+        caps, hits, drawn, table=caption_table,
+        first_seen_order=_first_seen_order(sample_indices, n_images, (caption_table or caption_feature_table(caps))[1]))
     aggregated["_bootstrap_values"] = {k: values[:, j].copy() for j, k in enumerate(METRIC_KEYS)}
     aggregated["_base_metrics"] = base_metrics(ranks)
     if tie_report:
@@ -507,20 +508,15 @@ def run_bootstrap_from_embeddings(img_embeds, t2i_txt_embeds, all_txt_embeds, m_
     return aggregated
 
 
-def _first_seen_order(sample_indices, n_images: int) -> np.ndarray:
-    """Base query indices in the order the reference's flattened per-iteration record list first meets them
-    (main.py:634,669-722: iteration 0 in sample order, then iteration 1, ...): the insertion order of
-    ``accuracy_by_category`` in the ``_failure_analysis`` cell. Only the leading iterations are read back (all of them
-    for small problems); queries they never drew follow in index order."""
+def _first_seen_order(sample_indices, n_images: int, cats) -> List[int]:
+    """Queries that introduce a category, in the reference's record order (failure.category_first_seen). Only the leading
+    iterations are read back from the device (all of them for small problems)."""
+    from .failure import category_first_seen
     B = int(sample_indices.shape[0])
     rows = B if B * n_images <= (1 << 20) else min(B, 8)
     head = sample_indices[:rows]
     head = head.cpu().numpy() if isinstance(head, torch.Tensor) else np.asarray(head)
-    flat = head.reshape(-1).astype(np.int64)
-    _, first = np.unique(flat, return_index=True)
-    seen = flat[np.sort(first)]
-    rest = np.setdiff1d(np.arange(n_images, dtype=np.int64), seen, assume_unique=False)
-    return np.concatenate([seen, rest])
+    return category_first_seen(head, cats)
 
 
 class FlatMultiVector:

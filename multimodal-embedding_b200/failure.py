@@ -98,6 +98,33 @@ def caption_feature_table(captions: Sequence[str]):
     return table
 
 
+def category_first_seen(draw_rows: np.ndarray, cats: Sequence[Optional[str]]) -> List[int]:
+    """One query index per category, in the order the reference's flattened per-iteration record list first meets the
+    categories (main.py:634,669-722: iteration 0 in draw order, then iteration 1, ...) — the insertion order of
+    ``accuracy_by_category``. ``draw_rows`` int [k, N] are the leading iterations' draws; rows are consumed only until
+    every category has been met (almost always the first one)."""
+    names = sorted({c for c in cats if c})
+    if not names:
+        return []
+    code = {c: i for i, c in enumerate(names)}
+    cid = np.array([code[c] if c else -1 for c in cats], dtype=np.int64)
+    seen: List[int] = []
+    have = set()
+    for row in np.asarray(draw_rows).reshape(-1, np.asarray(draw_rows).shape[-1]):
+        row = row.astype(np.int64)
+        c = cid[row]
+        ok = c >= 0
+        u, first = np.unique(c[ok], return_index=True)
+        qs = row[ok][first]
+        for k in np.argsort(first):
+            if int(u[k]) not in have:
+                have.add(int(u[k]))
+                seen.append(int(qs[k]))
+        if len(have) == len(names):
+            break
+    return seen
+
+
 def aggregate_failure_from_hits(captions: Sequence[str], hits: np.ndarray, drawn: np.ndarray,
                                 first_seen_order: Optional[Sequence[int]] = None, table=None) -> Dict[str, Any]:
     """main.py:669-722 evaluated from per-BASE-query totals: ``hits[q]`` = number of (iteration, copy) records of
