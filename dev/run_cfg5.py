@@ -55,7 +55,7 @@ t_all = time.perf_counter()
 rows, hits, phases = [], [], []
 for m in range(args.models):
     t0 = time.perf_counter()
-    row, h, t = workloads.colpali_model(dev, NQ, ND, LQ, LD, args.iterations, seed=100 + m, sigma=2.7 + 0.1 * m, rng=rng,
+    row, h, t = workloads.colpali_model(dev, NQ, ND, LQ, LD, args.iterations, seed=100 + m, sigma=3.5 + 0.1 * m, rng=rng,
                                         name=f"model{m}")
     t["wall_ms"] = 1e3 * (time.perf_counter() - t0)
     rows.append(row)

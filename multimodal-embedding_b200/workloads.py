@@ -108,7 +108,7 @@ def cfg5_section(dev: torch.device, group=None, n_iterations: int = 1000, nq: in
     own vectors with 2 % of the entries perturbed (the cost of a test does not depend on the data). dev/run_cfg5.py runs
     the full seven-model, 42-test configuration."""
     world, rank = _world(group)
-    row, hits, t = colpali_model(dev, nq, nd, lq, ld, n_iterations, seed=11, sigma=3.0,
+    row, hits, t = colpali_model(dev, nq, nd, lq, ld, n_iterations, seed=11, sigma=3.8,
                                  rng=np.random.RandomState(42), group=group, name="cfg5-model")
     total_ms = _max_over_ranks(t["score_rank_bootstrap_ms"], dev, group)
     k2_ms = _max_over_ranks(t.get("maxsim_kernel_ms") or 0.0, dev, group)
