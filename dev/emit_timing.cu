@@ -36,7 +36,7 @@ int main(int argc, char** argv) {
     cudaMalloc(&rbase, recs * LT * 2 + 8);
     cudaMalloc(&ehead, recs * 16 + 16);
     cudaMemcpy(words, h.data(), n_words * 4, cudaMemcpyHostToDevice);
-    cudaFuncSetAttribute(emit_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RING * 4);
+    cudaFuncSetAttribute(emit_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (RING + RING_PAD) * 4);
     cudaEvent_t a, b, c2;
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
         cudaMemcpyToSymbol(g_emit_prof, zero, sizeof(zero));
         cudaMemcpyToSymbol(g_emit_round, zero, sizeof(zero));
         cudaEventRecord(a);
-        emit_long_kernel<<<1, LT, RING * 4>>>(words, n_words, n, P, lp, info, jout, rmask, rbase, ehead);
+        emit_long_kernel<<<1, LT, (RING + RING_PAD) * 4>>>(words, n_words, n, P, lp, info, jout, rmask, rbase, ehead);
         cudaEventRecord(b);
         if (lp.n_epochs > 0) extract_long_kernel<<<(unsigned)recs, LT>>>(words, n, lp, info, rmask, rbase, ehead, jout);
         cudaEventRecord(c2);

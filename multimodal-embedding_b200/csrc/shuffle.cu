@@ -274,6 +274,8 @@ emit_kernel(const uint32_t* __restrict__ words, long long n_words, int n1, long 
 // The raw words live in a shared-memory ring that cp.async refills a whole epoch ahead, the last 63 steps of a
 // permutation (masks below 64: a handful of words each) are walked by one thread.
 constexpr int RING = 57344;             // words of the ring (224 KB)
+constexpr int CLASSIFY_MIN_S = 9;       // segments shorter than this are simply walked again every round
+constexpr int RING_PAD = 64;            // copy of the ring's first words behind its end: a thread's segment never wraps
 constexpr int WCAP = RING - 8;          // longest window of one epoch
 constexpr int TAIL_W = 4096;            // words the warp tail may look at
 #ifndef MMX_S_MIN
@@ -351,15 +353,8 @@ __device__ __forceinline__ int bar_and_active(int pred, int nthreads) {
     return r;
 }
 
-// accepts of a run of words that starts with `a` accepts behind it: word accepted iff a <= i_hi - v
-__device__ __forceinline__ int walk_count(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int a) {
-#pragma unroll 4
-    for (int k = 0; k < n; ++k) {
-        const int d = i_hi - (int)(w[k] & M);
-        a += (a <= d) ? 1 : 0;
-    }
-    return a;
-}
+// The walks below run over ONE thread's segment: `n` consecutive words at w (the ring keeps a copy of its first RING_PAD
+// words behind its end, so a segment never wraps). Word k is accepted iff the accepts before it (a) are <= i_hi - (w[k] & M).
 // two independent runs at once (the lower and the upper end of a bracket)
 __device__ __forceinline__ void walk_count2(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int& a, int& b) {
 #pragma unroll 4
@@ -369,28 +364,52 @@ __device__ __forceinline__ void walk_count2(const uint32_t* __restrict__ w, int 
         b += (b <= d) ? 1 : 0;
     }
 }
-// two runs, recording which words the first one accepted (bit k0 + k of m)
-__device__ __forceinline__ void walk_count2_mask(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int& a, int& b,
-                                                 int k0, unsigned long long& m) {
+// two runs, recording the accept masks of both (32 words per mask half)
+__device__ __forceinline__ void walk_count2_masks(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int& a, int& b,
+                                                  unsigned long long& ma, unsigned long long& mb) {
+    uint32_t a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+    const int n0 = min(n, 32);
 #pragma unroll 4
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; k < n0; ++k) {
         const int d = i_hi - (int)(w[k] & M);
-        const int acc = (a <= d) ? 1 : 0;
-        a += acc;
-        b += (b <= d) ? 1 : 0;
-        m |= (unsigned long long)acc << (k0 + k);
+        const uint32_t acca = (a <= d) ? 1u : 0u, accb = (b <= d) ? 1u : 0u;
+        a += acca;
+        b += accb;
+        a0 |= acca << k;
+        b0 |= accb << k;
     }
+#pragma unroll 4
+    for (int k = 32; k < n; ++k) {
+        const int d = i_hi - (int)(w[k] & M);
+        const uint32_t acca = (a <= d) ? 1u : 0u, accb = (b <= d) ? 1u : 0u;
+        a += acca;
+        b += accb;
+        a1 |= acca << (k - 32);
+        b1 |= accb << (k - 32);
+    }
+    ma = (unsigned long long)a0 | ((unsigned long long)a1 << 32);
+    mb = (unsigned long long)b0 | ((unsigned long long)b1 << 32);
 }
-// the exact run: also records which words were accepted (bit k0 + k of m)
-__device__ __forceinline__ int walk_mask(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int a, int k0,
+// the exact run: also records which words were accepted
+__device__ __forceinline__ int walk_mask(const uint32_t* __restrict__ w, int n, uint32_t M, int i_hi, int a,
                                          unsigned long long& m) {
+    uint32_t m0 = 0, m1 = 0;
+    const int n0 = min(n, 32);
 #pragma unroll 4
-    for (int k = 0; k < n; ++k) {
+    for (int k = 0; k < n0; ++k) {
         const int d = i_hi - (int)(w[k] & M);
-        const int acc = (a <= d) ? 1 : 0;
+        const uint32_t acc = (a <= d) ? 1u : 0u;
         a += acc;
-        m |= (unsigned long long)acc << (k0 + k);
+        m0 |= acc << k;
     }
+#pragma unroll 4
+    for (int k = 32; k < n; ++k) {
+        const int d = i_hi - (int)(w[k] & M);
+        const uint32_t acc = (a <= d) ? 1u : 0u;
+        a += acc;
+        m1 |= acc << (k - 32);
+    }
+    m = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
     return a;
 }
 
@@ -398,7 +417,7 @@ __global__ void __launch_bounds__(LT, 1)
 emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, int P,
                  const __grid_constant__ LongPlan plan, long long* __restrict__ info, int32_t* __restrict__ jout,
                  unsigned long long* __restrict__ rmask, uint16_t* __restrict__ rbase, long long* __restrict__ ehead) {
-    extern __shared__ uint32_t ring[];  // [RING] word g of the stream sits at ring[g % RING]
+    extern __shared__ uint32_t ring[];  // [RING + RING_PAD] word g of the stream sits at ring[g % RING]
     __shared__ uint32_t wtot[2][LT / 32];
     __shared__ int s_end;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -421,6 +440,7 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
             const uint32_t* src = words + loaded + 4 * tid;
             for (int g = 4 * tid; g < cnt; g += 4 * LT) {
                 cp_async16(ring + r, src);
+                if (r < RING_PAD) cp_async16(ring + RING + r, src);
                 src += 4 * LT;
                 r += 4 * LT;
                 if (r >= RING) r -= RING;
@@ -457,12 +477,18 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
                     const int t0 = min(W, tid * S), len = min(W, t0 + S) - t0;
                     int r0 = pos_mod + t0;
                     if (r0 >= RING) r0 -= RING;
-                    const int len1 = min(len, RING - r0);  // words before the ring wraps
-                    const uint32_t* w1 = ring + r0;
-                    const uint32_t* w2 = ring + (r0 + len1 - RING);  // == ring when the segment wraps
+                    const uint32_t* seg = ring + r0;  // contiguous thanks to the ring's padding
                     int Lb = 0, Ub = t0, cnt = 0;
                     bool have_cnt = false, have_mask = false;  // the segment's accept count / accept mask is final
                     unsigned long long acc_mask = 0;
+                    // classified segment: every word is surely accepted (mask sure_m, sure_n of them), surely rejected, or
+                    // one of at most UNC uncertain words e[j] = theta | k << 16 (word k accepted iff start + uncertain
+                    // accepts before it <= theta)
+                    constexpr int UNC = 4;
+                    bool cls = false;
+                    unsigned long long sure_m = 0;
+                    int sure_n = 0, un = 0;
+                    uint32_t e0 = 0, e1 = 0, e2 = 0, e3 = 0;
                     for (int rnd = 0;; ++rnd) {
                         EMIT_CLOCK(ra);
                         uint32_t pk;  // low half: a lower bound of this segment's accepts, high half: an upper bound
@@ -470,32 +496,73 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
                             pk = (uint32_t)len << 16;  // behind the epoch's end: nothing depends on it
                         } else if (have_cnt) {
                             pk = (uint32_t)cnt | ((uint32_t)cnt << 16);
-                        } else if (Lb == Ub) {  // exact base: the walk is the serial simulation of the segment
-                            acc_mask = 0;
-                            int a = walk_mask(w1, len1, M, i_hi, Lb, 0, acc_mask);
-                            a = walk_mask(w2, len - len1, M, i_hi, a, len1, acc_mask);
-                            cnt = a - Lb;
-                            have_cnt = have_mask = true;
-                            pk = (uint32_t)cnt | ((uint32_t)cnt << 16);
-                        } else {
-                            // accepts are non-increasing in the start value: a run from Ub bounds them from below, a
-                            // run from Lb from above. A run from anywhere in between stays between the two, so when
-                            // they accept the same number of words they accept the SAME words, and so does every run
-                            // from a narrower bracket: the segment's count (and mask) is final from then on
-                            int lo = Ub, hi = Lb;
-                            if (rnd >= 2) {  // brackets are narrow by now: most segments freeze here, keep the mask
-                                acc_mask = 0;
-                                walk_count2_mask(w1, len1, M, i_hi, lo, hi, 0, acc_mask);
-                                walk_count2_mask(w2, len - len1, M, i_hi, lo, hi, len1, acc_mask);
-                            } else {
-                                walk_count2(w1, len1, M, i_hi, lo, hi);
-                                walk_count2(w2, len - len1, M, i_hi, lo, hi);
+                        } else if (cls) {
+                            // two runs over the uncertain words only
+                            int xa = Ub, xb = Lb;
+                            const uint32_t ee[UNC] = {e0, e1, e2, e3};
+#pragma unroll
+                            for (int j = 0; j < UNC; ++j)
+                                if (j < un) {
+                                    const int th = (int)(ee[j] & 0xffffu);
+                                    xa += (xa <= th) ? 1 : 0;
+                                    xb += (xb <= th) ? 1 : 0;
+                                }
+                            const int cl = sure_n + xa - Ub, cu = sure_n + xb - Lb;
+                            pk = (uint32_t)cl | ((uint32_t)cu << 16);
+                            if (cl == cu) {  // the same uncertain words are accepted from both ends: final
+                                acc_mask = sure_m;
+                                int x = Lb;
+#pragma unroll
+                                for (int j = 0; j < UNC; ++j)
+                                    if (j < un && x <= (int)(ee[j] & 0xffffu)) {
+                                        acc_mask |= 1ull << (ee[j] >> 16);
+                                        ++x;
+                                    }
+                                cnt = cl;
+                                have_cnt = have_mask = true;
                             }
+                        } else if (rnd == 0 || S < CLASSIFY_MIN_S) {
+                            // accepts are non-increasing in the start value: a run from Ub bounds them from below, a
+                            // run from Lb from above. (Every lane of the warp takes the same kind of walk in a round:
+                            // a warp that mixes walk kinds pays for each of them.)
+                            int lo = Ub, hi = Lb;
+                            walk_count2(seg, len, M, i_hi, lo, hi);
                             pk = (uint32_t)(lo - Ub) | ((uint32_t)(hi - Lb) << 16);
-                            if (lo - Ub == hi - Lb) {
+                            if (rnd > 0 && lo - Ub == hi - Lb) {  // short segments: frozen as soon as both runs agree
                                 cnt = hi - Lb;
                                 have_cnt = true;
-                                have_mask = rnd >= 2;
+                            }
+                        } else {
+                            // the brackets are narrow from the second round on. A run from anywhere inside the bracket
+                            // stays between the run from Lb and the run from Ub: words both accept are accepted from
+                            // everywhere in the bracket (and every narrower one: the brackets are nested), words both
+                            // reject are rejected, the FEW others are kept with their thresholds — no full walk again
+                            int lo = Ub, hi = Lb;
+                            unsigned long long mU = 0, mL = 0;
+                            walk_count2_masks(seg, len, M, i_hi, lo, hi, mU, mL);
+                            pk = (uint32_t)(lo - Ub) | ((uint32_t)(hi - Lb) << 16);
+                            unsigned long long unc = mL & ~mU;
+                            if (unc == 0ull) {
+                                acc_mask = mU;
+                                cnt = hi - Lb;
+                                have_cnt = have_mask = true;
+                            } else if (__popcll(unc) <= UNC) {
+                                cls = true;
+                                sure_m = mU;
+                                sure_n = lo - Ub;
+                                un = 0;
+                                while (unc != 0ull) {
+                                    const int k = __ffsll((long long)unc) - 1;
+                                    unc &= unc - 1ull;
+                                    const int d = i_hi - (int)(seg[k] & M);
+                                    const uint32_t ent =
+                                        (uint32_t)(d - __popcll(mU & ((1ull << k) - 1ull))) | ((uint32_t)k << 16);
+                                    if (un == 0) e0 = ent;
+                                    else if (un == 1) e1 = ent;
+                                    else if (un == 2) e2 = ent;
+                                    else e3 = ent;
+                                    ++un;
+                                }
                             }
                         }
                         EMIT_CLOCK(rb);
@@ -525,10 +592,7 @@ emit_long_kernel(const uint32_t* __restrict__ words, long long n_words, int n, i
                     EMIT_CLOCK(tc2);
                     EMIT_ADD(e, 1, tc2 - tc1);
                     if (Lb < c && !have_mask) {  // frozen before the masks were kept: one exact walk
-                        acc_mask = 0;
-                        int a = walk_mask(w1, len1, M, i_hi, Lb, 0, acc_mask);
-                        a = walk_mask(w2, len - len1, M, i_hi, a, len1, acc_mask);
-                        cnt = a - Lb;
+                        cnt = walk_mask(seg, len, M, i_hi, Lb, acc_mask) - Lb;
                     }
                     // ---- record: the j values themselves (the k-th accepted word of the epoch is the j of step
                     // i_hi - k) are pulled out of the word stream by all SMs afterwards (extract_long_kernel) from this
@@ -927,7 +991,7 @@ extern "C" int mmx_perm_shuffle(const uint32_t* words, int64_t n_words, int n, i
         // n > MAX_N: the emit is one CTA that is parallel within a permutation (bracketing prefix sums per mask epoch),
         // the swaps are resolved per position by a pointer chase, the composition keeps its rows in shared memory
         const LongPlan lp = make_long_plan(n);
-        const size_t smem_long = (size_t)RING * 4;
+        const size_t smem_long = (size_t)(RING + RING_PAD) * 4;
         static const char long_attr_tag = 0;
         if (first_use_on_device(&long_attr_tag)) {
             MMX_CHECK_CUDA(cudaFuncSetAttribute(emit_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
