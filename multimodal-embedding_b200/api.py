@@ -629,6 +629,7 @@ def _maxsim_streamed(qv: FlatMultiVector, dv: FlatMultiVector, dev: torch.device
 
 
 BITMASK_LIMIT_BYTES = 16 << 30     # above-GT bitmasks larger than this switch the dense path to LIST mode
+MAXSIM_SCORES_LIMIT = 2 << 30      # single-GPU MaxSim score matrices larger than this are never materialised (ops.maxsim_rank)
 
 
 def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: Dict, n_iterations: int, rng=None,
@@ -724,7 +725,17 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     gt_idx = _np_h2d(q2d, dev, torch.int32)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     # ---- score + threshold pass on this rank's shard (async)
-    if colpali:
+    fused_rank = colpali and world == 1 and 4 * nq * n_local > MAXSIM_SCORES_LIMIT
+    if fused_rank:
+        # one GPU and a score matrix that would not be small: score + rank block by block, no [nq, n_docs] matrix
+        q_flat, _ = qv.to_device(dev)
+        d_flat, d_off = dv.to_device(dev)
+        fl = _pad_flags(dv.lens)
+        ev[0].record()
+        local = ops.maxsim_rank(q_flat, qv.lens, d_flat, d_off, gt_off, gt_idx,
+                                _np_h2d(fl, dev, torch.uint8) if fl.any() else None, g_base=0)
+        ev[1].record()
+    elif colpali:
         ev[0].record()
         S = _maxsim_streamed(qv, dv, dev, shard_flags, group=group if world > 1 else None)
         ev[1].record()
@@ -743,7 +754,9 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
                          torch.int32)
     marks.append(("score_queued", time.perf_counter()))
     thr = sharded.merge_thresholds(local.thr, group)
-    if colpali:
+    if fused_rank:
+        pass                                             # thresholds, counts and bit rows are already there
+    elif colpali:
         local = ops.rank_from_scores(S, gt_off, gt_idx, g_base=g_base, thr=thr)
     elif list_mode:
         local = ops.dense_rank_lists(Q, G, gt_off, gt_idx, g_base=g_base, thr=thr, cap=list_cap or ops.LIST_CAP)

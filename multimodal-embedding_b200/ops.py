@@ -120,6 +120,49 @@ def maxsim_scores(q_tok: torch.Tensor, q_off: torch.Tensor, d_tok: torch.Tensor,
     return out
 
 
+MAXSIM_RANK_BLOCK_BYTES = 1 << 30   # score block of the fused MaxSim ranking (queries per block = this / (4 n_docs))
+
+
+def maxsim_rank(q_tok: torch.Tensor, q_lens, d_tok: torch.Tensor, d_off: torch.Tensor, gt_off: torch.Tensor,
+                gt_idx: torch.Tensor, d_zero: Optional[torch.Tensor] = None, want_bits: bool = True, g_base: int = 0,
+                block_bytes: Optional[int] = None) -> ProtocolRanks:
+    """K2 + KR without the [n_queries, n_docs] score matrix (SURVEY 8b ``mmx_maxsim_rank``; main.py:467 + :331-358): the
+    queries are scored in blocks of whole queries into ONE reusable block buffer (<= block_bytes), each block is ranked
+    at once — thresholds from its ground-truth columns, then strict-greater counts and bitmask rows — and its scores are
+    dropped. A 25 000 x 100 000 problem needs 1 GB of scores at a time instead of 10 GB; the patches are re-read once
+    per block (12 x 26 GB = 50 ms of HBM time against 11 s of tensor work). Same kernels; a block's queries sit at other
+    rows of the 128-row tiles than in a whole-matrix call (another fixed fp32 summation tree), so scores can differ in the
+    last bit — thresholds and counts are taken from the SAME block scores, the ranking is self-consistent. For an
+    UNSHARDED document set: both ranking passes run on a block while its scores
+    exist, which needs every ground-truth column to be local (sharded callers keep their 1/N-size matrix instead).
+    q_lens: host int array of tokens per query (the blocks are cut on the host)."""
+    _need_cuda(q_tok, d_tok, d_off, gt_off, gt_idx, d_zero)
+    lens = np.asarray(q_lens, dtype=np.int64)
+    nq, nd = len(lens), d_off.numel() - 1
+    off_h = np.zeros(nq + 1, dtype=np.int64)
+    off_h[1:] = np.cumsum(lens)
+    dev = q_tok.device
+    thr, cnt, bits, wpr = _alloc_rank(nq, nd, dev, want_bits)
+    per = max(1, int((block_bytes or MAXSIM_RANK_BLOCK_BYTES) // max(1, 4 * nd)))
+    buf = torch.empty((min(per, nq), nd), dtype=torch.float32, device=dev)
+    h = _lib.lib()
+    q_off_all = torch.from_numpy(off_h.astype(np.int32)).to(dev)
+    for a in range(0, nq, per):
+        b = min(nq, a + per)
+        S = buf[: b - a]
+        sub_off = (q_off_all[a:b + 1] - int(off_h[a])).contiguous()
+        maxsim_scores(q_tok[int(off_h[a]):int(off_h[b])], sub_off, d_tok, d_off, d_zero, out=S)
+        # this block's rows of the GT structure: offsets rebased, column ids unchanged
+        g0 = gt_off[a:b + 1]
+        go = (g0 - g0[:1]).contiguous()
+        gi = gt_idx[int(g0[0].item()):int(g0[-1].item())].contiguous() if a or b < nq else gt_idx
+        for mode in (MODE_THRESHOLD, MODE_COUNT):
+            _lib.check(h.mmx_rank_from_scores(S.data_ptr(), b - a, nd, S.stride(0), go.data_ptr(), gi.data_ptr(), g_base, mode,
+                                              thr[a:b].data_ptr(), cnt[a:b].data_ptr() if mode else None,
+                                              bits[a:b].data_ptr() if (mode and bits is not None) else None, wpr, _stream()))
+    return ProtocolRanks(thr=thr, cnt_above=cnt, bits=bits, n_cols=nd)
+
+
 def _alloc_rank(nq: int, n_cols: int, device, want_bits: bool):
     thr = torch.full((nq,), float("-inf"), dtype=torch.float32, device=device)
     cnt = torch.zeros((nq,), dtype=torch.int32, device=device)

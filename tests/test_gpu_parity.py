@@ -882,6 +882,65 @@ def test_perm_stats_long_vectors_bit_exact(mmx_mod, n1, n2):
     assert np.array_equal(d, w)
 
 
+def test_maxsim_rank_without_the_score_matrix(mmx_mod, monkeypatch):
+    """ops.maxsim_rank (score + rank block by block, SURVEY 8b mmx_maxsim_rank) gives the thresholds, counts and bitmask
+    of scoring the whole matrix and ranking it (thresholds to fp32 rounding, integers identical) and run_retrieval_bootstrap takes it for large single-GPU
+    problems with the same row."""
+    dev = _dev()
+    docs, queries = synth_colpali(90, 450, doc_len=70, q_len=(5, 19), sigma_q=2.5, seed=21, ragged_docs=(30, 80))
+    docs[7] = -docs[7].abs()
+    queries[40] = queries[40].abs()
+    q2d = np.arange(450) // 5
+    api = mmx_mod.api
+    q_flat, q_off, q_lens = api._flatten(queries, dev)
+    d_flat, d_off, d_lens = api._flatten(docs, dev)
+    flags = api._pad_flags(d_lens)
+    dz = torch.from_numpy(flags).to(dev)
+    gt_off = torch.arange(451, dtype=torch.int32, device=dev)
+    gt_idx = torch.from_numpy(q2d.astype(np.int32)).to(dev)
+    S = mmx_mod.ops.maxsim_scores(q_flat, q_off, d_flat, d_off, dz)
+    want = mmx_mod.ops.rank_from_scores(S, gt_off, gt_idx)
+    for block_bytes in (4 * 90 * 7, 4 * 90 * 100, 1 << 30):            # 7 queries per block, 100, all at once
+        got = mmx_mod.ops.maxsim_rank(q_flat, q_lens, d_flat, d_off, gt_off, gt_idx, dz, block_bytes=block_bytes)
+        # a block's queries sit at other rows of the 128-row tiles than in the whole-matrix call: another (fixed) fp32
+        # summation tree, so the thresholds agree to rounding; counts and bit rows come from the same block scores
+        assert torch.allclose(got.thr, want.thr, rtol=2e-6, atol=0)
+        assert torch.equal(got.cnt_above, want.cnt_above) and torch.equal(got.bits, want.bits)
+    thr_o, cnt_o, _ = oracle.above_gt_counts(oracle.maxsim_scores(queries, docs), [[int(c)] for c in q2d])
+    assert torch.equal(got.cnt_above.cpu().long(), cnt_o)
+    m_info = {"type": "colpali", "name": "c"}
+    ref = mmx_mod.run_retrieval_bootstrap(queries, docs, q2d, m_info, 60, rng=np.random.RandomState(5))
+    monkeypatch.setattr(api, "MAXSIM_SCORES_LIMIT", 0)
+    monkeypatch.setattr(mmx_mod.ops, "MAXSIM_RANK_BLOCK_BYTES", 4 * 90 * 33)
+    got = mmx_mod.run_retrieval_bootstrap(queries, docs, q2d, m_info, 60, rng=np.random.RandomState(5))
+    assert got["base"] == ref["base"] and np.array_equal(got["_bootstrap_values"], ref["_bootstrap_values"])
+    assert all(got[k] == ref[k] for k in ref if k.startswith("R@"))
+
+
+def test_place_bit_columns_matches_the_torch_merge(mmx_mod):
+    """mmx_place_bit_columns (ONE all-gather shard merge, counts = popcounts) against the host-logic torch merge, for
+    shards that start inside 32-column words, empty shards and widths that are not multiples of 32."""
+    dev = _dev()
+    rs = np.random.RandomState(3)
+    for bounds in ([(0, 37), (37, 37), (37, 101), (101, 230)], [(0, 625), (625, 1250)], [(0, 5), (5, 6), (6, 70)], [(0, 64)]):
+        nq, n_cols = 57, bounds[-1][1]
+        above = rs.rand(nq, n_cols) < 0.3
+        wmax = max((e - b + 31) // 32 for b, e in bounds)
+        parts = []
+        for b, e in bounds:
+            pad = np.zeros((nq, wmax * 32), dtype=np.uint8)
+            pad[:, : e - b] = above[:, b:e]
+            pad[:, e - b:] = rs.rand(nq, wmax * 32 - (e - b)) < 0.5          # garbage beyond the shard's width is ignored
+            parts.append(torch.from_numpy(np.packbits(pad, axis=1, bitorder="little").view(np.int32).copy()))
+        gathered = torch.stack(parts).to(dev)
+        bits, cnt = mmx_mod.ops.place_bit_columns(gathered, bounds)
+        full = np.zeros((nq, (n_cols + 31) // 32 * 32), dtype=np.uint8)
+        full[:, :n_cols] = above
+        want = np.packbits(full, axis=1, bitorder="little").view(np.int32)
+        assert np.array_equal(bits.cpu().numpy(), want)
+        assert np.array_equal(cnt.cpu().numpy(), above.sum(1).astype(np.int32))
+
+
 def test_run_bootstrap_benchmark_reference_signature(mmx_mod):
     """main.py:478-667 through the drop-in signature, with stand-ins for the upstream pieces it keeps (dataset walk,
     image cache, encoders): items without an image or with fewer than five captions are skipped exactly like
