@@ -706,7 +706,7 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         list_mode = (not colpali) and nq * n_docs // 8 > BITMASK_LIMIT_BYTES
     if list_mode and colpali:
         raise ValueError("LIST mode applies to the dense path (the MaxSim path materialises its score matrix)")
-    split_stats = world > 1 and DEVICE_RNG and not list_mode   # LIST mode's recount round trips stay on rank 0
+    split_stats = world > 1 and DEVICE_RNG
     if rank == 0 or split_stats:
         if DEVICE_RNG:
             drng = ops.DeviceRng(r, dev)
@@ -768,7 +768,7 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     if keep is not None:
         keep["ranks"] = ranks
     if not split_stats:
-        # one GPU, LIST mode (exact-recount round trips) and the host-RNG mode keep the statistics on rank 0
+        # one GPU and the host-RNG mode keep the statistics on rank 0
         if rank != 0:
             if list_mode:
                 sharded.unlisted_round(recount, None, None, group)           # serve rank 0's recount, if there is one
@@ -795,7 +795,9 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         torch.cuda.current_stream().wait_event(rng_done)
         for t in (sample_indices, ci_idx):
             t.record_stream(torch.cuda.current_stream())
-        values, means = sharded.bootstrap_stats(ranks, sample_indices, ci_idx, gt_idx, n_docs, group)
+        k3_stats = {}
+        boot_fn = sharded.list_boot_fn(recount, group, k3_stats) if list_mode else None
+        values, means = sharded.bootstrap_stats(ranks, sample_indices, ci_idx, gt_idx, n_docs, group, boot_fn=boot_fn)
         if rank != 0:
             return None
     marks.append(("stats_queued", time.perf_counter()))

@@ -454,12 +454,10 @@ def boot_counts(r: ProtocolRanks, mult: torch.Tensor, list_len: int = LIST_LEN,
     return correct
 
 
-def boot_counts_lists(r: ProtocolRanks, mult: torch.Tensor, resolve, q_hits1: Optional[torch.Tensor] = None,
-                      list_len: Optional[int] = None, stats: Optional[dict] = None) -> torch.Tensor:
-    """K3 in LIST mode: `r` from dense_rank_lists (per-shard lists stacked along dim 0 after the all-gather, cnt_above
-    = the shard-summed exact counts). Pairs the truncated lists cannot settle are recounted exactly through
-    `resolve(pairs[n, 2], mult_rows) -> c[n]` (dense_unlisted_resolver; sharded.unlisted_round across gallery shards)
-    and added back: the result equals the bitmask path bit for bit."""
+def boot_counts_lists_raw(r: ProtocolRanks, mult: torch.Tensor, q_hits1: Optional[torch.Tensor] = None,
+                          list_len: Optional[int] = None):
+    """K3 in LIST mode without the exact recount: returns (correct int32 [B, 3] WITHOUT the unsettled pairs' share,
+    pairs int32 [n, 2] (iteration, query) the truncated lists could not settle — None when there are none)."""
     _need_cuda(mult, r.list_i, r.list_n, r.cnt_above)
     n_shards, nq, cap = r.list_i.shape
     L = cap if list_len is None else min(list_len, cap)
@@ -485,19 +483,41 @@ def boot_counts_lists(r: ProtocolRanks, mult: torch.Tensor, resolve, q_hits1: Op
         unres_cap = n_un                                  # more unsettled pairs than room: run again with enough
     if q_hits1 is not None:
         q_hits1.copy_(hits)
+    return correct, (unres[:n_un] if n_un else None)
+
+
+def unlisted_request(pairs: torch.Tensor, mult: torch.Tensor):
+    """What an exact recount needs for the unsettled pairs: (pairs with the iteration replaced by a row index into
+    mult_rows, mult_rows = only those iterations' multiplicity rows)."""
+    b_used, b_pos = torch.unique(pairs[:, 0], return_inverse=True)
+    return torch.stack([b_pos.to(torch.int32), pairs[:, 1]], dim=1), mult[b_used.long()].contiguous()
+
+
+def apply_unlisted(correct: torch.Tensor, pairs: torch.Tensor, c: torch.Tensor, r: ProtocolRanks, mult: torch.Tensor,
+                   q_hits1: Optional[torch.Tensor] = None) -> None:
+    """Add the exactly recounted pairs' share to `correct` in place: min(m_q, max(0, k - c)) per pair."""
+    B, dev = correct.shape[0], correct.device
+    b, q = pairs[:, 0].long(), pairs[:, 1].long()
+    mq = mult[b, q if r.q_unit is None else r.q_unit[q].long()].long()
+    for col, k in enumerate((1, 5, 10)):
+        add = torch.minimum(mq, (k - c).clamp_min(0))
+        correct[:, col] += torch.zeros(B, dtype=torch.int64, device=dev).index_add_(0, b, add).to(torch.int32)
+        if k == 1 and q_hits1 is not None:
+            q_hits1 += torch.zeros(r.nq, dtype=torch.int64, device=dev).index_add_(0, q, add).to(q_hits1.dtype)
+
+
+def boot_counts_lists(r: ProtocolRanks, mult: torch.Tensor, resolve, q_hits1: Optional[torch.Tensor] = None,
+                      list_len: Optional[int] = None, stats: Optional[dict] = None) -> torch.Tensor:
+    """K3 in LIST mode: `r` from dense_rank_lists (per-shard lists stacked along dim 0 after the all-gather, cnt_above
+    = the shard-summed exact counts). Pairs the truncated lists cannot settle are recounted exactly through
+    `resolve(pairs[n, 2], mult_rows) -> c[n]` (dense_unlisted_resolver; sharded.unlisted_round across gallery shards)
+    and added back: the result equals the bitmask path bit for bit."""
+    correct, pairs = boot_counts_lists_raw(r, mult, q_hits1, list_len)
     if stats is not None:
-        stats["unresolved_pairs"] = n_un
-    if n_un:
-        pairs = unres[:n_un]
-        b_used, b_pos = torch.unique(pairs[:, 0], return_inverse=True)     # only these iterations' multiplicity rows travel
-        c = resolve(torch.stack([b_pos.to(torch.int32), pairs[:, 1]], dim=1), mult[b_used.long()].contiguous())
-        b, q = pairs[:, 0].long(), pairs[:, 1].long()
-        mq = mult[b, q if r.q_unit is None else r.q_unit[q].long()].long()
-        for col, k in enumerate((1, 5, 10)):
-            add = torch.minimum(mq, (k - c).clamp_min(0))
-            correct[:, col] += torch.zeros(B, dtype=torch.int64, device=dev).index_add_(0, b, add).to(torch.int32)
-            if k == 1 and q_hits1 is not None:
-                q_hits1 += torch.zeros(nq, dtype=torch.int64, device=dev).index_add_(0, q, add).to(q_hits1.dtype)
+        stats["unresolved_pairs"] = 0 if pairs is None else int(pairs.shape[0])
+    if pairs is not None:
+        c = resolve(*unlisted_request(pairs, mult))
+        apply_unlisted(correct, pairs, c, r, mult, q_hits1)
     return correct
 
 

@@ -15,7 +15,7 @@ work on any torch.distributed backend (nccl on the B200s, gloo in the CPU tests)
 """
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -95,7 +95,7 @@ def _popcount_rows(bits: torch.Tensor) -> torch.Tensor:
     return torch.from_numpy(np.unpackbits(u8, axis=1).sum(axis=1).astype(np.int32))
 
 
-def unlisted_round(local_resolve, pairs, mult_rows, group=None) -> torch.Tensor:
+def unlisted_round(local_resolve, pairs, mult_rows, group=None, src_rank: int = 0) -> torch.Tensor:
     """The exact recount of LIST-mode K3's unsettled (iteration, query) pairs across gallery shards. Rank 0 (which ran
     K3) passes the pairs and the multiplicity rows they refer to, every other rank None; EVERY rank calls this once
     per K3 call (rank 0 with pairs=None when nothing was left unsettled). The pairs and rows are broadcast, each
@@ -103,16 +103,16 @@ def unlisted_round(local_resolve, pairs, mult_rows, group=None) -> torch.Tensor:
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local_resolve(pairs, mult_rows) if pairs is not None else None
     rank = dist.get_rank(group)
-    src = dist.get_global_rank(group, 0) if group is not None else 0
+    src = dist.get_global_rank(group, src_rank) if group is not None else src_rank
     dev = mult_rows.device if mult_rows is not None else _group_device(group)
     head = torch.zeros(3, dtype=torch.int64, device=dev)
-    if rank == 0 and pairs is not None:
+    if rank == src_rank and pairs is not None:
         head = torch.tensor([pairs.shape[0], mult_rows.shape[0], mult_rows.shape[1]], dtype=torch.int64, device=dev)
     dist.broadcast(head, src=src, group=group)
     n, r, u = (int(x) for x in head.tolist())
     if n == 0:
         return None
-    if rank != 0:
+    if rank != src_rank:
         pairs = torch.empty((n, 2), dtype=torch.int32, device=dev)
         mult_rows = torch.empty((r, u), dtype=torch.uint8, device=dev)
     pairs, mult_rows = pairs.contiguous(), mult_rows.contiguous()
@@ -164,6 +164,37 @@ def gather_rows(host_rows: torch.Tensor, dev: torch.device, group=None) -> torch
         mine[: b - a].copy_(host_rows[a:b], non_blocking=True)
     dist.all_gather(list(out.view(world, per, *host_rows.shape[1:]).unbind(0)), mine, group=group)
     return out[:n]
+
+
+def list_boot_fn(recount, group=None, stats: Optional[dict] = None):
+    """boot_fn for bootstrap_stats in LIST mode (split over ranks): K3 on the lists for this rank's iteration block, then
+    ONE tiny all-reduce asks whether any rank has pairs its truncated lists could not settle (probability ~1e-17 each at
+    cap 64); only then every rank's pairs are recounted exactly, rank by rank, over all gallery shards (unlisted_round)."""
+    from . import ops
+
+    def fn(ranks: ProtocolRanks, mult: torch.Tensor) -> torch.Tensor:
+        correct, pairs = ops.boot_counts_lists_raw(ranks, mult)
+        n_mine = 0 if pairs is None else int(pairs.shape[0])
+        flag = torch.tensor([n_mine], dtype=torch.int64, device=mult.device)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
+            tot = flag.clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=group)
+            n_all = int(tot.item())
+        else:
+            n_all = n_mine
+        if stats is not None:
+            stats["unresolved_pairs"] = n_all
+        if n_all:
+            rank = dist.get_rank(group) if world > 1 else 0
+            for r in range(world):
+                mine = rank == r and pairs is not None
+                req = ops.unlisted_request(pairs, mult) if mine else (None, None)
+                c = unlisted_round(recount, req[0], req[1], group, src_rank=r)
+                if mine:
+                    ops.apply_unlisted(correct, pairs, c, ranks, mult)
+        return correct
+    return fn
 
 
 def bootstrap_stats(ranks: ProtocolRanks, sample_indices: torch.Tensor, ci_idx: torch.Tensor, q_unit: torch.Tensor,
