@@ -43,6 +43,7 @@
 // of the tile. Two reducer warps (2 and 3,
 // one per accumulator) sum the rows of a whole tile's documents at once, two lanes per document, instead of one
 // latency-bound shuffle tree per document.
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cstdlib>
@@ -101,6 +102,8 @@ struct __align__(1024) Smem {
     int seg_q[2][BM];
     uint64_t a_full, a_free;
     uint64_t b_full[NSTAGE], b_empty[NSTAGE];
+    uint64_t pb_full[4], pb_empty[4];  // CTA-pair kernel: 4 half-size B stages
+    uint64_t t_full4[4], t_empty4[4];  // CTA-pair kernel: four 128-column accumulator slots [accumulator][column half]
     uint64_t t_full[2], t_empty[2];
     uint64_t st_full[2][NSLOT], st_empty[2][NSLOT];
     uint64_t batch_full[2][2], batch_empty[2][2];  // SHORT, [accumulator][buffer]: M written by the 4 drain warps / consumed by the reducer
@@ -149,6 +152,10 @@ struct EpiCtx {
     Smem* s;
     const Params* p;
     int half, lane, row, d1;
+    // CTA-pair kernel: the accumulators are handed back to the LEADER CTA's MMA thread — shared::cluster addresses of
+    // its t_empty barriers (0 = this CTA's own barrier, the one-CTA kernels)
+    uint32_t t_empty_cluster[2];
+    uint64_t* t_full[2];  // "accumulator a is complete" for the columns this warp drains
 };
 
 // cur_doc is complete for this thread's columns: park the row maximum for the reducer and move to the next doc.
@@ -228,16 +235,19 @@ __device__ __forceinline__ void skip_to(const EpiCtx& c, Walk& w, int g, int pen
     while (!w.done && w.cur_end <= pend) close_doc(c, w, g);
 }
 
-__device__ __forceinline__ void release_accumulator(Smem& s, int a, int lane) {
+__device__ __forceinline__ void release_accumulator(const EpiCtx& c, Smem& s, int a, int lane) {
     // this warp's 128 columns are in registers: hand the accumulator back to the MMA warp
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&s.t_empty[a]);
+    if (lane == 0) {
+        if (c.t_empty_cluster[a] != 0u) mbar_arrive_cluster(c.t_empty_cluster[a]);
+        else mbar_arrive(&s.t_empty[a]);
+    }
 }
 
 // Drain this warp's 128 columns of accumulator `a` for the B tile that starts at patch `pt`.
 __device__ __forceinline__ void drain_accumulator(const EpiCtx& c, Smem& s, Walk& w, int a, uint32_t t_lane, int pt) {
-    mbar_wait(&s.t_full[a], w.use & 1);
+    mbar_wait(c.t_full[a], w.use & 1);
     w.use++;
     tc_fence_after();
     const uint32_t ta = t_lane + a * BN;
@@ -257,7 +267,7 @@ __device__ __forceinline__ void drain_accumulator(const EpiCtx& c, Smem& s, Walk
         tmem_ld_32x32(ta + 96, vb);
         m = max32(va, m);
         tmem_ld_wait();
-        release_accumulator(s, a, c.lane);
+        release_accumulator(c, s, a, c.lane);
         w.m = max32(vb, m);
     } else {
         // a document (or the chunk of documents) ends inside this tile; closing a document costs a shared-memory
@@ -273,7 +283,7 @@ __device__ __forceinline__ void drain_accumulator(const EpiCtx& c, Smem& s, Walk
         tmem_ld_32x32(ta + 96, vb);
         fold_chunk_general(c, w, a, va, pc0 + 64);
         tmem_ld_wait();
-        release_accumulator(s, a, c.lane);
+        release_accumulator(c, s, a, c.lane);
         fold_chunk_general(c, w, a, vb, pc0 + 96);
         if (c.half == 0) skip_to(c, w, a, pt + BN);
     }
@@ -683,7 +693,10 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                         tmem_ld_32x16(ta + 16 * (st + NBUF - 1), va[(st + NBUF - 1) % NBUF]);
                         tmem_ld_32x16(ta + 128 + 16 * (st + NBUF - 1), vb[(st + NBUF - 1) % NBUF]);
                     } else if (st + NBUF - 1 == 8) {
-                        release_accumulator(s, a, lane);  // all 256 columns of this row are in registers
+                        // all 256 columns of this row are in registers
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s.t_empty[a]);
                     }
                     fold_short2(va[st % NBUF], vb[st % NBUF], m, mB, (elo >> (4 * st)) & 0xfu, (ehi >> (4 * st)) & 0xfu,
                                 addrA, addrB);
@@ -706,6 +719,9 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         c.s = &s;
         c.p = &p;
         c.half = (warp - 4) >> 2;  // which 128 columns of every accumulator this warp drains
+        c.t_empty_cluster[0] = c.t_empty_cluster[1] = 0u;
+        c.t_full[0] = &s.t_full[0];
+        c.t_full[1] = &s.t_full[1];
         c.lane = lane;
         c.row = (warp & 3) * 32 + lane;  // TMEM lane quarter = warp % 4
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + c.half * HALF_COLS;
@@ -739,6 +755,232 @@ maxsim_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------------------- CTA-pair variant
+// The same pipeline on a cluster of two CTAs (one TPC) with tcgen05 cta_group::2: the pair works on ONE chunk of
+// documents and FOUR 128-row query tiles (two per CTA). Every B tile of 256 patches is split — each CTA's TMA fetches
+// 128 of them into its own shared memory — and one `tcgen05.mma.cta_group::2` (M = 256: 128 rows of each CTA, N = 256)
+// issued by the leader CTA fills the same accumulator in both CTAs' TMEM: every CTA pulls half the B bytes from L2 and
+// its tensor core reads half the B rows from its own shared memory, the other half arrives from the peer. Everything
+// behind the accumulators (drain warps, reducer, carry) is per CTA and unchanged.
+//   barriers (all in the LEADER's shared memory unless noted): a_full / pb_full[stage] count the TMA bytes of BOTH CTAs
+//   (the peer's loads complete on the leader's barrier); the accumulators are FOUR slots of 128 columns
+//   [row tile][column half], each drained by 4 + 4 warps of the two CTAs that arrive on the leader's t_empty4[slot]
+//   (the peer's over the cluster); tcgen05.commit multicasts t_full4[slot], pb_empty[stage] and a_free to both CTAs.
+// With half-size B stages the ring is 4 deep in the same shared memory.
+constexpr int PSTAGE = 4;
+constexpr int BP_ROWS = BN / 2;                    // patches per CTA and B tile
+constexpr int BP_HALF_BYTES = BP_ROWS * 128;       // one 64-wide K half: 16 KB
+constexpr int BP_STAGE_BYTES = 2 * BP_HALF_BYTES;  // 32 KB
+static_assert(PSTAGE * BP_STAGE_BYTES == NSTAGE * B_STAGE_BYTES, "the pair kernel reuses the B ring's shared memory");
+
+struct PairGeom {
+    int mp, nm, nm_pair, d0, d1, p0, p1, ntiles;
+};
+__device__ __forceinline__ PairGeom pair_geom(const Params& p, int item, int n_mpp, int rank) {
+    PairGeom g;
+    const int mpp = item % n_mpp, ch = item / n_mpp;
+    g.mp = 2 * mpp + rank;
+    g.nm = max(0, min(2, p.n_mtiles - 2 * g.mp));          // this CTA's valid row tiles (the last pair may be ragged)
+    g.nm_pair = max(0, min(2, p.n_mtiles - 4 * mpp));      // the leader's: MMAs are issued for these accumulators
+    g.d0 = ch * p.docs_per_chunk;
+    g.d1 = min(p.nd, g.d0 + p.docs_per_chunk);
+    g.p0 = __ldg(p.d_off + g.d0);
+    g.p1 = __ldg(p.d_off + g.d1);
+    g.ntiles = (g.p1 - g.p0 + BN - 1) / BN;
+    return g;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+maxsim_pair_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
+                   const __grid_constant__ Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    uint8_t* const bring = &s.b[0][0];  // [PSTAGE][2 K halves][128 rows x 128 B]
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_d);
+    }
+    if (warp == 1 && elect_one()) {
+        mbar_init(&s.a_full, 1);
+        mbar_init(&s.a_free, 1);
+        for (int i = 0; i < PSTAGE; ++i) {
+            mbar_init(&s.pb_full[i], 1);
+            mbar_init(&s.pb_empty[i], 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(&s.t_full4[i], 1);
+            mbar_init(&s.t_empty4[i], 8);  // 4 drain warps of each CTA (only the leader's copy is used)
+        }
+        for (int i = 0; i < 2; ++i) {
+            for (int j = 0; j < NSLOT; ++j) {
+                mbar_init(&s.st_full[i][j], 8);
+                mbar_init(&s.st_empty[i][j], 1);
+            }
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_2cta(&s.tmem_base, TMEM_COLS);
+        tmem_relinquish_2cta();
+    }
+    tc_fence_before();
+    cluster_sync_all();  // both CTAs' barriers are initialised before anything arrives on them remotely
+    tc_fence_after();
+    const uint32_t tmem_base = s.tmem_base;
+    const int n_mpp = (p.n_mpairs + 1) / 2;
+    const int n_items = n_mpp * p.n_chunks;
+    const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (one per CTA)
+        if (elect_one()) {
+            const uint32_t a_full_leader = mapa_shared(smem_u32(&s.a_full), 0);
+            uint32_t it = 0, bcount = 0;
+            for (int item = cl; item < n_items; item += ncl, ++it) {
+                const PairGeom g = pair_geom(p, item, n_mpp, rank);
+                if (it > 0) mbar_wait(&s.a_free, (it - 1) & 1);
+                if (leader) mbar_arrive_expect_tx(&s.a_full, 2 * 2 * A_TILE_BYTES);
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_2d_2cta(s.a[m] + h * A_HALF_BYTES, &tmap_q, a_full_leader, h * 64, (g.mp * 2 + m) * BM);
+                for (int t = 0; t < g.ntiles; ++t, ++bcount) {
+                    const uint32_t st = bcount % PSTAGE, ph = (bcount / PSTAGE) & 1;
+                    mbar_wait(&s.pb_empty[st], ph ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&s.pb_full[st], 2 * BP_STAGE_BYTES);
+                    const uint32_t full_leader = mapa_shared(smem_u32(&s.pb_full[st]), 0);
+                    // this CTA's 64 + 64 patches of the tile: rows [0, 64) of its stage pair up with the peer's rows
+                    // [0, 64) into the tile's first 128 columns, rows [64, 128) into the second 128
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+#pragma unroll
+                        for (int part = 0; part < 2; ++part)
+                            tma_load_2d_2cta(bring + st * BP_STAGE_BYTES + h * BP_HALF_BYTES + part * (BP_ROWS / 2) * 128,
+                                             &tmap_d, full_leader, h * 64,
+                                             g.p0 + t * BN + part * (BN / 2) + (int)rank * (BP_ROWS / 2));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread of the leader CTA)
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN / 2);
+            uint32_t it = 0, bcount = 0, use[4] = {0, 0, 0, 0};
+            for (int item = cl; item < n_items; item += ncl, ++it) {
+                const PairGeom g = pair_geom(p, item, n_mpp, rank);
+                mbar_wait(&s.a_full, it & 1);
+                tc_fence_after();
+                for (int t = 0; t < g.ntiles; ++t, ++bcount) {
+                    const uint32_t st = bcount % PSTAGE, ph = (bcount / PSTAGE) & 1;
+                    mbar_wait(&s.pb_full[st], ph);
+                    tc_fence_after();
+                    // four accumulator slots of 128 columns: a slot is written again three MMA groups (~1500 clk) after
+                    // it completed, which covers the drain plus the peer's remote release
+                    for (int m = 0; m < g.nm_pair; ++m)
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {
+                            const int slot = 2 * m + hf;
+                            mbar_wait(&s.t_empty4[slot], (use[slot] & 1) ^ 1);
+                            tc_fence_after();
+#pragma unroll
+                            for (int k = 0; k < DIM / 16; ++k) {
+                                const uint32_t a_addr = smem_u32(s.a[m] + (k >> 2) * A_HALF_BYTES) + (k & 3) * 32;
+                                const uint32_t b_addr = smem_u32(bring + st * BP_STAGE_BYTES + (k >> 2) * BP_HALF_BYTES +
+                                                                 hf * (BP_ROWS / 2) * 128) + (k & 3) * 32;
+                                umma_bf16_ss_2cta(tmem_base + m * BN + hf * (BN / 2), umma_desc_kmajor_sw128(a_addr),
+                                                  umma_desc_kmajor_sw128(b_addr), idesc, k > 0);
+                            }
+                            umma_commit_2cta(&s.t_full4[slot]);
+                            use[slot]++;
+                        }
+                    umma_commit_2cta(&s.pb_empty[st]);
+                }
+                umma_commit_2cta(&s.a_free);
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ reducer (per CTA, as in the one-CTA kernel)
+        Reducer r[2];
+        r[0].nposted = r[1].nposted = 0;
+        for (int item = cl; item < n_items; item += ncl) {
+            const PairGeom g = pair_geom(p, item, n_mpp, rank);
+            int cur[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int mt = g.mp * 2 + a;
+                const int r0 = mt * BM;
+                r[a].mt = mt;
+                r[a].cont_first = (r0 > 0) && (r0 < p.n_qtok) && (__ldg(p.tok2q + r0 - 1) == __ldg(p.tok2q + r0));
+                r[a].nseg = (a < g.nm) ? build_segments(s, p, a, mt, lane) : 0;
+                cur[a] = (a < g.nm) ? g.d0 : g.d1;
+            }
+            for (int t = 0; t < g.ntiles; ++t) {
+                const int pend = g.p0 + (t + 1) * BN;
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+                    while (cur[a] < g.d1 && __ldg(p.d_off + cur[a] + 1) <= pend) {
+                        reduce_doc(s, p, r[a], a, cur[a], lane);
+                        cur[a]++;
+                    }
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+                while (cur[a] < g.d1) {  // trailing documents without patches
+                    reduce_doc(s, p, r[a], a, cur[a], lane);
+                    cur[a]++;
+                }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ drain warps (8 warps per CTA)
+        EpiCtx c;
+        c.s = &s;
+        c.p = &p;
+        c.half = (warp - 4) >> 2;
+        c.lane = lane;
+        c.row = (warp & 3) * 32 + lane;
+        c.t_empty_cluster[0] = mapa_shared(smem_u32(&s.t_empty4[0 + c.half]), 0);
+        c.t_empty_cluster[1] = mapa_shared(smem_u32(&s.t_empty4[2 + c.half]), 0);
+        c.t_full[0] = &s.t_full4[0 + c.half];
+        c.t_full[1] = &s.t_full4[2 + c.half];
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + c.half * HALF_COLS;
+        Walk w0, w1;
+        w0.nposted = w1.nposted = 0;
+        w0.use = w1.use = 0;
+        for (int item = cl; item < n_items; item += ncl) {
+            const PairGeom g = pair_geom(p, item, n_mpp, rank);
+            c.d1 = g.d1;
+            const int e0 = __ldg(p.d_off + g.d0 + 1);
+            const int e1 = (g.d0 + 1 < g.d1) ? __ldg(p.d_off + g.d0 + 2) : e0;
+            w0.cur_doc = w1.cur_doc = g.d0;
+            w0.cur_end = w1.cur_end = e0;
+            w0.next_end = w1.next_end = e1;
+            w0.m = w1.m = -INFINITY;
+            // a row tile beyond the matrix (ragged last pair) is still drained — the MMA wrote it and waits for its
+            // release — but closes no documents
+            w0.done = (g.d0 >= g.d1) || (g.nm < 1);
+            w1.done = (g.d0 >= g.d1) || (g.nm < 2);
+#pragma unroll 1
+            for (int t = 0; t < g.ntiles; ++t) {
+                const int pt = g.p0 + t * BN;
+                if (g.nm_pair >= 1) drain_accumulator(c, s, w0, 0, t_lane, pt);
+                if (g.nm_pair == 2) drain_accumulator(c, s, w1, 1, t_lane, pt);
+            }
+            while (!w0.done) close_doc(c, w0, 0);
+            while (!w1.done) close_doc(c, w1, 1);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer may still be reading this CTA's shared memory / writing its TMEM through the pair MMA
+    if (warp == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
 }
 
 // tok2q[t] = query that owns token row t (binary search in q_off).
@@ -960,10 +1202,25 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
     }
     const long long n_items = (long long)p.n_mpairs * p.n_chunks;
     const int grid = (int)(n_items < sms ? n_items : sms);
-    if (wp.shortdocs)
+    // CTA-pair variant (long documents): two CTAs of a TPC share every B tile through tcgen05 cta_group::2
+    static const int pair_mode = [] {
+        const char* e = getenv("MMX_MAXSIM_PAIR");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    const long long n_items_pair = (long long)((p.n_mpairs + 1) / 2) * p.n_chunks;
+    if (wp.shortdocs) {
         maxsim_kernel<true><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, td, p);
-    else
+    } else if (pair_mode != 0 && p.n_mtiles >= 4 && n_items_pair >= sms / 2) {
+        CUtensorMap td_half;
+        if (make_tmap_bf16_sw128(&td_half, d_mat, (uint64_t)(d_rows > 0 ? d_rows : 1), DIM, DIM, BP_ROWS / 2) != 0) return -4;
+        static const char pair_attr_tag = 0;
+        if (first_use_on_device(&pair_attr_tag))
+            MMX_CHECK_CUDA(cudaFuncSetAttribute(maxsim_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        const int grid_pair = (int)std::min<long long>(2 * n_items_pair, sms & ~1);
+        maxsim_pair_kernel<<<grid_pair, NUM_THREADS, smem_bytes, stream>>>(tq, td_half, p);
+    } else {
         maxsim_kernel<false><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, td, p);
+    }
     MMX_CHECK_CUDA(cudaGetLastError());
 
     if (p.n_mtiles > 1) {
