@@ -390,7 +390,7 @@ def run_ours(args):
                         "written back to numpy; wall clock, max over ranks"},
         "gpu_launches": launches_per_step * K,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "mmx::maxsim::maxsim_kernel", "achieved": achieved_tf,
+        "roofline": {"bound": "tensor", "kernel": "mmx::maxsim::maxsim_pair_kernel (tcgen05 cta_group::2)", "achieved": achieved_tf,
                      "peak": pk["bf16"], "unit": "TFLOP/s", "frac": achieved_tf / pk["bf16"],
                      "frac_of_sustained_peak": achieved_tf / pk["bf16_sustained"] if pk["bf16_sustained"] else None,
                      "peak_source": pk["source"] + "; burst cuBLAS figure", "kernel_ms": k2_ms,

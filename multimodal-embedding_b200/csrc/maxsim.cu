@@ -1203,9 +1203,9 @@ extern "C" int mmx_maxsim_scores(const void* q_tok, const int32_t* q_off, int64_
     const long long n_items = (long long)p.n_mpairs * p.n_chunks;
     const int grid = (int)(n_items < sms ? n_items : sms);
     // CTA-pair variant (long documents): two CTAs of a TPC share every B tile through tcgen05 cta_group::2
-    static const int pair_mode = [] {
+    static const int pair_mode = [] {  // on by default; MMX_MAXSIM_PAIR=0 selects the one-CTA kernel (dev/check_pair.py)
         const char* e = getenv("MMX_MAXSIM_PAIR");
-        return e != nullptr ? atoi(e) : 0;
+        return e != nullptr ? atoi(e) : 1;
     }();
     const long long n_items_pair = (long long)((p.n_mpairs + 1) / 2) * p.n_chunks;
     if (wp.shortdocs) {
