@@ -501,6 +501,28 @@ def dense_section(dev, K, W, cpu_iters=2):
     e1.record()
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1) / K
+    # the same step as ONE CUDA graph (the eager step is ~30 launches of kernels that take microseconds: launch-bound)
+    graph_ms = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            graph_out = step()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(graph_out, step()), "graph replay and eager step disagree"
+        e0.record()
+        for _ in range(K):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_ms = e0.elapsed_time(e1) / K
+    except Exception as exc:  # noqa: BLE001 - the eager number stands on its own
+        graph_ms = f"capture failed: {type(exc).__name__}: {exc}"[:200]
     # K1 on its own: the ranking (COUNT) pass of the I2T protocol, 5000 x 25000 x 1152, against the bf16 peak
     gt_off = torch.arange(0, 5 * N + 1, 5, dtype=torch.int32, device=dev)
     gt_idx = torch.arange(5 * N, dtype=torch.int32, device=dev)
@@ -554,7 +576,12 @@ def dense_section(dev, K, W, cpu_iters=2):
                "first_iterations_equal_gpu_row": bool(same)}
     return {"cpu_baseline": cpu, "workload": "SigLIP-400M dense scoring 5000x1152 / 25000x1152, T2I + I2T(1-to-5) + I2T_Sym, "
                         "1000-iter bootstrap + 9 CIs (10 000 resamples each)",
-            "metric": "dense_score_rank_bootstrap_wall_ms", "device_resident_ms": dev_ms, "e2e_ms": e2e_ms,
+            "metric": "dense_score_rank_bootstrap_wall_ms", "device_resident_ms": dev_ms,
+            "device_resident_cuda_graph_ms": graph_ms,
+            "frac_of_bf16_peak_whole_step": {"eager": 2.0 * pairs * Dm / (dev_ms * 1e-3) / 1e12 / peaks()["bf16"],
+                                            "cuda_graph": (2.0 * pairs * Dm / (graph_ms * 1e-3) / 1e12 / peaks()["bf16"]
+                                                           if isinstance(graph_ms, float) else None)},
+            "e2e_ms": e2e_ms,
             "k1_count_pass": {"shape": "5000 x 25000 x 1152 (I2T ranking pass, bitmask written)", "ms": k1_ms,
                               "tflops": k1_tf, "frac_of_bf16_peak": k1_tf / peaks()["bf16"],
                               "note": f"{k1_iters} back-to-back launches incl. the host-side allocation of their outputs"},

@@ -21,6 +21,7 @@
 // with its own full/empty barrier: half 0 finishes 512 clk before half 1, its four epilogue warps drain it while the
 // tensor core is still busy with half 1, and the next tile's half-0 MMAs start as soon as they are done.
 // Warp roles: 0 = TMA, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue of half 0, 8..11 = epilogue of half 1.
+#include <algorithm>
 #include <cfloat>
 #include <cuda_bf16.h>
 
@@ -74,10 +75,18 @@ struct Params {
     long long nq, ng;
     int kblocks, n_mblk, n_ntile, n_tiles, mode;
     int band;                   // 256-row tiles per raster band: concurrent CTAs share A and B tiles through L2
+    int n_mpair, band_pair, n_tiles_pair;  // CTA-pair kernels: the same raster over 512-row tile pairs
 };
+
+// CTA-pair kernels (tcgen05 cta_group::2): a stage holds this CTA's two A halves and 128 of the 256 gallery rows
+constexpr int PSTAGE = 4;
+constexpr int BP_BYTES = (BN / 2) * 128;                  // 16 KB
+constexpr int PSTAGE_BYTES = 2 * A_BYTES + BP_BYTES;      // 48 KB
+static_assert(PSTAGE * PSTAGE_BYTES <= NSTAGE * STAGE_BYTES, "the pair kernels reuse the ring's shared memory");
 
 struct __align__(1024) Smem {
     uint8_t stage[NSTAGE][STAGE_BYTES];
+    uint64_t pfull[PSTAGE], pempty[PSTAGE];   // pair kernels
     uint64_t full[NSTAGE], empty[NSTAGE];
     uint64_t t_full[2], t_empty[2];
     uint32_t tmem_base;
@@ -90,6 +99,15 @@ __device__ __forceinline__ void tile_coords(const Params& p, int t, int& m_blk, 
     const int rows = min(p.band, p.n_mblk - band * p.band);
     n_tile = rem / rows;
     m_blk = band * p.band + rem % rows;
+}
+// the same raster over 512-row tile PAIRS (pair kernels): m_pair = index of the pair of 256-row tiles
+__device__ __forceinline__ void tile_coords_pair(const Params& p, int t, int& m_pair, int& n_tile) {
+    const int per_band = p.band_pair * p.n_ntile;
+    const int band = t / per_band;
+    const int rem = t - band * per_band;
+    const int rows = min(p.band_pair, p.n_mpair - band * p.band_pair);
+    n_tile = rem / rows;
+    m_pair = band * p.band_pair + rem % rows;
 }
 __device__ __forceinline__ int tile_id(const Params& p, int i) {
     return p.tile_list != nullptr ? __ldg(p.tile_list + i) : i;
@@ -124,7 +142,13 @@ __device__ __forceinline__ void flush_pending(const Params& p, uint32_t (&bits)[
 
 // MODE is a template parameter: each pass gets an epilogue without the other passes' code (the threshold pass
 // indexes the accumulator registers dynamically, which would put the COUNT pass's registers on the stack too).
-template <int MODE, int FEAT = MMX_FEAT_NONE>
+// PAIR = true: launched as clusters of two CTAs (one TPC). The pair owns a 512 x 256 output tile — 256 rows per CTA —
+// and every 256-row gallery block is split: each CTA's TMA fetches 128 of its rows (completing on the leader's barrier)
+// and one tcgen05.mma.cta_group::2 (M = 256: 128 rows of each CTA, N = 256) issued by the leader fills the same
+// accumulator half in both CTAs' TMEM, so every CTA pulls 48 KB instead of 64 KB per K block from L2. Epilogues are per
+// CTA and unchanged; their releases arrive on the leader's t_empty (the peer's through the cluster), the MMA commits are
+// multicast to both CTAs. Not used for the threshold pass (a compacted list of single tiles).
+template <int MODE, int FEAT = MMX_FEAT_NONE, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_g,
                   const __grid_constant__ Params p) {
@@ -132,6 +156,11 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    // work distribution: CTAs (or CTA pairs) stride over the tile list
+    const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&tmap_q);
@@ -142,23 +171,80 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             mbar_init(&s.full[i], 1);
             mbar_init(&s.empty[i], 1);
         }
+        for (int i = 0; i < PSTAGE; ++i) {
+            mbar_init(&s.pfull[i], 1);
+            mbar_init(&s.pempty[i], 1);
+        }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&s.t_full[i], 1);
-            mbar_init(&s.t_empty[i], 4);
+            mbar_init(&s.t_empty[i], PAIR ? 8 : 4);   // pair: the four epilogue warps of this half in BOTH CTAs
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(&s.tmem_base, TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc_2cta(&s.tmem_base, TMEM_COLS);
+            tmem_relinquish_2cta();
+        } else {
+            tmem_alloc(&s.tmem_base, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
-    const int n_work = p.n_tiles_dev != nullptr ? __ldg(p.n_tiles_dev) : p.n_tiles;
+    const int n_work = PAIR ? p.n_tiles_pair : (p.n_tiles_dev != nullptr ? __ldg(p.n_tiles_dev) : p.n_tiles);
+    uint8_t* const pring = &s.stage[0][0];   // pair kernels: [PSTAGE][A0 | A1 | B half]
 
-    if (warp == 0) {
+    if (warp == 0 && PAIR) {
+        if (elect_one()) {
+            uint32_t kc = 0;
+            for (int i = w_first; i < n_work; i += w_step) {
+                int m_pair, n_tile;
+                tile_coords_pair(p, i, m_pair, n_tile);
+                const int m_blk = 2 * m_pair + (int)rank;
+                for (int kb = 0; kb < p.kblocks; ++kb, ++kc) {
+                    const uint32_t st = kc % PSTAGE, ph = (kc / PSTAGE) & 1;
+                    mbar_wait(&s.pempty[st], ph ^ 1);
+                    if (leader) mbar_arrive_expect_tx(&s.pfull[st], 2 * PSTAGE_BYTES);
+                    const uint32_t full_leader = mapa_shared(smem_u32(&s.pfull[st]), 0);
+                    uint8_t* dst = pring + st * PSTAGE_BYTES;
+                    tma_load_2d_2cta(dst, &tmap_q, full_leader, kb * BK, m_blk * TM);
+                    tma_load_2d_2cta(dst + A_BYTES, &tmap_q, full_leader, kb * BK, m_blk * TM + BM);
+                    tma_load_2d_2cta(dst + 2 * A_BYTES, &tmap_g, full_leader, kb * BK, n_tile * BN + (int)rank * (BN / 2));
+                }
+            }
+        }
+    } else if (warp == 1 && PAIR) {
+        if (leader && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+            uint32_t kc = 0, tc = 0;
+            for (int i = w_first; i < n_work; i += w_step, ++tc) {
+                for (int kb = 0; kb < p.kblocks; ++kb, ++kc) {
+                    const uint32_t st = kc % PSTAGE, ph = (kc / PSTAGE) & 1;
+                    mbar_wait(&s.pfull[st], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(pring + st * PSTAGE_BYTES);
+                    const uint32_t b_addr = a_addr + 2 * A_BYTES;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (kb == 0) {  // the epilogue warps of this half (both CTAs) have drained the previous tile
+                            mbar_wait(&s.t_empty[h], (tc & 1) ^ 1);
+                            tc_fence_after();
+                        }
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_ss_2cta(tmem_base + h * BN, umma_desc_kmajor_sw128(a_addr + h * A_BYTES + k * 32),
+                                              umma_desc_kmajor_sw128(b_addr + k * 32), idesc, (kb | k) != 0);
+                        if (kb == p.kblocks - 1) umma_commit_2cta(&s.t_full[h]);
+                    }
+                    umma_commit_2cta(&s.pempty[st]);
+                }
+            }
+        }
+    } else if (warp == 0) {
         if (elect_one()) {
             uint32_t kc = 0;
             for (int i = blockIdx.x; i < n_work; i += gridDim.x) {
@@ -211,9 +297,15 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) pend_bits[c] = 0u;
         int pend_base = 0, pend_m = 0, pend_nt = 0;  // reserved slots, row tile and column tile of those hits
-        for (int i = blockIdx.x; i < n_work; i += gridDim.x, ++tc) {
+        const uint32_t t_empty_leader = PAIR ? mapa_shared(smem_u32(&s.t_empty[acc]), 0) : 0u;
+        for (int i = w_first; i < n_work; i += w_step, ++tc) {
             int m_blk, n_tile;
-            tile_coords(p, tile_id(p, i), m_blk, n_tile);
+            if (PAIR) {
+                tile_coords_pair(p, i, m_blk, n_tile);
+                m_blk = 2 * m_blk + (int)rank;
+            } else {
+                tile_coords(p, tile_id(p, i), m_blk, n_tile);
+            }
             const uint32_t use = tc;
             const long long q = (long long)m_blk * TM + row;
             const long long n0 = (long long)n_tile * BN;
@@ -261,7 +353,10 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     // the whole accumulator half is in registers: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&s.t_empty[acc]);
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(t_empty_leader);
+                        else mbar_arrive(&s.t_empty[acc]);
+                    }
                 }
                 const long long c0 = n0 + ch * 32;
                 if (MODE == MMX_MODE_GROUPMAX) {
@@ -362,8 +457,13 @@ dense_rank_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) {
+        cluster_sync_all();  // the peer's tensor core may still read this CTA's shared memory / write its TMEM
+        if (warp == 2) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+    } else {
+        __syncthreads();
+        if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    }
 }
 
 // MODE_THRESHOLD work list: ids of the (row tile, column tile) pairs that contain at least one GT column.
@@ -397,14 +497,45 @@ extern "C" int mmx_dense_workspace_bytes(int64_t nq, int64_t ng, size_t* bytes) 
     return 0;
 }
 
+// 0 = one-CTA kernels, 1 (default) = CTA pairs when the sweep has at least one wave of pair tiles, 2 = pairs whenever possible
+static int dense_pair_mode() {
+    static const int mode = [] {
+        const char* e = getenv("MMX_DENSE_PAIR");
+        return e != nullptr ? atoi(e) : 1;
+    }();
+    return mode;
+}
+
 template <int MODE, int FEAT>
-static int launch_variant(const CUtensorMap& tq, const CUtensorMap& tg, const Params& p, cudaStream_t stream) {
+static int launch_variant(const CUtensorMap& tq, const CUtensorMap& tg, const CUtensorMap& tg_half, const Params& p,
+                          cudaStream_t stream) {
     const size_t smem_bytes = sizeof(Smem) + 1024;
+    const int sms = sm_count();
+    const int pm = dense_pair_mode();
+    if (MODE != MMX_MODE_THRESHOLD && pm != 0 && p.n_tiles_pair >= (pm >= 2 ? 1 : sms / 2)) {
+        static const char pair_attr_tag = 0;  // one per template instantiation
+        if (first_use_on_device(&pair_attr_tag))
+            MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MODE, FEAT, true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)std::min(2 * p.n_tiles_pair, sms & ~1));
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MMX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dense_rank_kernel<MODE, FEAT, true>, tq, tg_half, p));
+        return 0;
+    }
     static const char attr_set_tag = 0;  // one per template instantiation
     if (first_use_on_device(&attr_set_tag))
         MMX_CHECK_CUDA(cudaFuncSetAttribute(dense_rank_kernel<MODE, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)smem_bytes));
-    const int sms = sm_count();
     const int grid = p.n_tiles < sms ? p.n_tiles : sms;
     dense_rank_kernel<MODE, FEAT><<<grid, NUM_THREADS, smem_bytes, stream>>>(tq, tg, p);
     MMX_CHECK_CUDA(cudaGetLastError());
@@ -413,22 +544,23 @@ static int launch_variant(const CUtensorMap& tq, const CUtensorMap& tg, const Pa
 
 static int launch_dense(const void* Q, int64_t nq, const void* G, int64_t ng, int d, const Params& p,
                         cudaStream_t stream) {
-    CUtensorMap tq, tg;
+    CUtensorMap tq, tg, th;
     if (make_tmap_bf16_sw128(&tq, Q, (uint64_t)nq, (uint64_t)d, (uint64_t)d, BM) != 0) return -4;
     if (make_tmap_bf16_sw128(&tg, G, (uint64_t)ng, (uint64_t)d, (uint64_t)d, BN) != 0) return -4;
-    if (p.mode == MMX_MODE_THRESHOLD) return launch_variant<MMX_MODE_THRESHOLD, MMX_FEAT_NONE>(tq, tg, p, stream);
-    if (p.mode == MMX_MODE_GROUPMAX) return launch_variant<MMX_MODE_GROUPMAX, MMX_FEAT_NONE>(tq, tg, p, stream);
-    if (p.mode == MMX_MODE_LISTS) return launch_variant<MMX_MODE_LISTS, MMX_FEAT_NONE>(tq, tg, p, stream);
+    if (make_tmap_bf16_sw128(&th, G, (uint64_t)ng, (uint64_t)d, (uint64_t)d, BN / 2) != 0) return -4;   // pair kernels
+    if (p.mode == MMX_MODE_THRESHOLD) return launch_variant<MMX_MODE_THRESHOLD, MMX_FEAT_NONE>(tq, tg, th, p, stream);
+    if (p.mode == MMX_MODE_GROUPMAX) return launch_variant<MMX_MODE_GROUPMAX, MMX_FEAT_NONE>(tq, tg, th, p, stream);
+    if (p.mode == MMX_MODE_LISTS) return launch_variant<MMX_MODE_LISTS, MMX_FEAT_NONE>(tq, tg, th, p, stream);
     // MMX_MODE_COUNT: at most one optional output per pass
     const int n_opt = (p.grp_max != nullptr) + (p.cand_n != nullptr) + (p.scores != nullptr);
     MMX_REQUIRE(n_opt <= 1, "COUNT pass: group maxima, candidates and scores are mutually exclusive");
-    if (p.grp_max != nullptr) return launch_variant<MMX_MODE_COUNT, MMX_FEAT_GRP>(tq, tg, p, stream);
+    if (p.grp_max != nullptr) return launch_variant<MMX_MODE_COUNT, MMX_FEAT_GRP>(tq, tg, th, p, stream);
     if (p.cand_n != nullptr) {
         MMX_REQUIRE(p.cand_s != nullptr && p.cand_i != nullptr, "candidate buffers missing");
-        return launch_variant<MMX_MODE_COUNT, MMX_FEAT_CAND>(tq, tg, p, stream);
+        return launch_variant<MMX_MODE_COUNT, MMX_FEAT_CAND>(tq, tg, th, p, stream);
     }
-    if (p.scores != nullptr) return launch_variant<MMX_MODE_COUNT, MMX_FEAT_SCORES>(tq, tg, p, stream);
-    return launch_variant<MMX_MODE_COUNT, MMX_FEAT_NONE>(tq, tg, p, stream);
+    if (p.scores != nullptr) return launch_variant<MMX_MODE_COUNT, MMX_FEAT_SCORES>(tq, tg, th, p, stream);
+    return launch_variant<MMX_MODE_COUNT, MMX_FEAT_NONE>(tq, tg, th, p, stream);
 }
 
 static int base_params(Params& p, int64_t nq, int64_t ng, int d) {
@@ -443,6 +575,9 @@ static int base_params(Params& p, int64_t nq, int64_t ng, int d) {
     p.n_tiles = (int)(n_mblk * n_ntile);
     long long band = BAND_BYTES / ((long long)TM * d * 2);
     p.band = (int)(band < 8 ? 8 : (band > 64 ? 64 : band));
+    p.n_mpair = (int)((n_mblk + 1) / 2);
+    p.band_pair = std::max(4, p.band / 2);
+    p.n_tiles_pair = (int)((long long)p.n_mpair * n_ntile);
     return 0;
 }
 
