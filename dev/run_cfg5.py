@@ -32,6 +32,8 @@ ap.add_argument("--docs", type=int, default=100000)
 ap.add_argument("--queries", type=int, default=25000)
 ap.add_argument("--iterations", type=int, default=1000)
 ap.add_argument("--check-host", type=int, default=1)
+ap.add_argument("--prefetch", type=int, default=1, help="replay the per-query tests' shuffles on rank 0 while ranks 1.. score "
+                "(rank 0 then holds no documents); 0 = every rank scores, the tests run afterwards")
 args = ap.parse_args()
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -51,12 +53,25 @@ torch.cuda.synchronize()
 torch.cuda.reset_peak_memory_stats()
 
 rng = np.random.RandomState(42)          # the reference's one global stream (SEED = 42, main.py:99)
+n_pairs = args.models * (args.models - 1) // 2
+prefetch = bool(args.prefetch) and world > 1
+bounds = None
+pre = None
 t_all = time.perf_counter()
+if prefetch:
+    # numpy's stream does not depend on the data: rank 0 replays the shuffles of the 21 per-query tests (they follow the seven
+    # models' bootstrap draws in the stream) while ranks 1.. score the documents
+    from mmx import sharded
+    bounds = [(0, 0)] + sharded.shard_bounds(ND, world - 1)
+    if rank == 0:
+        pre = mmx.ops.ShufflePrefetch(rng, [(2 * NQ, 10000)] * n_pairs, dev,
+                                      skip=lambda d: [mmx.api.skip_bootstrap_draws(d, ND, args.iterations)
+                                                      for _ in range(args.models)]).start()
 rows, hits, phases = [], [], []
 for m in range(args.models):
     t0 = time.perf_counter()
-    row, h, t = workloads.colpali_model(dev, NQ, ND, LQ, LD, args.iterations, seed=100 + m, sigma=3.5 + 0.1 * m, rng=rng,
-                                        name=f"model{m}")
+    row, h, t = workloads.colpali_model(dev, NQ, ND, LQ, LD, args.iterations, seed=100 + m, sigma=3.6 + 0.005 * m, rng=rng,
+                                        name=f"model{m}", bounds=bounds)
     t["wall_ms"] = 1e3 * (time.perf_counter() - t0)
     rows.append(row)
     hits.append(h)
@@ -75,42 +90,58 @@ if world > 1:
 
 out = None
 if rank == 0:
-    tests = {"per_iteration_n2000": [], "per_query_n50000": []}
+    tests = {"per_query_n50000": [], "per_iteration_n2000": []}
     t_tests = time.perf_counter()
-    check = args.check_host
-    for i in range(args.models):
-        for j in range(i + 1, args.models):
-            for kind, a, b in (("per_iteration_n2000", rows[i]["_bootstrap_values"][:, 0], rows[j]["_bootstrap_values"][:, 0]),
-                               ("per_query_n50000", hits[i], hits[j])):
-                ref_p = None
-                if kind == "per_query_n50000" and check > 0:
-                    # the reference itself (main.py:281-302) on a copy of the generator
-                    g2 = np.random.RandomState()
-                    g2.set_state(rng.get_state())
-                    obs = np.abs(np.mean(a) - np.mean(b))
-                    comb = np.concatenate([a, b])
-                    diffs = []
-                    for _ in range(10000):
-                        g2.shuffle(comb)
-                        diffs.append(np.abs(np.mean(comb[:len(a)]) - np.mean(comb[len(a):])))
-                    ref_p = float(np.mean(np.array(diffs) >= obs))
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                p = mmx.permutation_test(a, b, rng=rng)
-                torch.cuda.synchronize()
-                rec = {"pair": [i, j], "p": float(p), "ms": 1e3 * (time.perf_counter() - t0)}
-                if ref_p is not None:
-                    rec["reference_p"] = ref_p
-                    g3 = np.random.RandomState()
-                    g3.set_state(rng.get_state())
-                    rec["same_p_and_generator_state"] = bool(ref_p == float(p) and g2.randint(0, 1 << 30) == g3.randint(0, 1 << 30))
-                    check -= 1
-                tests[kind].append(rec)
+    pairs = [(i, j) for i in range(args.models) for j in range(i + 1, args.models)]
+    if pre is not None:
+        assert pre.starts_where(rng), "the dry run of the bootstrap draws does not match what the models consumed"
+    # ---- per-query Recall@1 vectors (n = 2 x 25 000) first, then the per-iteration arrays (n = 2 x 1000)
+    for k, (i, j) in enumerate(pairs):
+        a, b = hits[i], hits[j]
+        ref_p = g2 = None
+        if k < args.check_host:
+            # the reference itself (main.py:281-302) with numpy's own shuffles, from the same stream position
+            g2 = np.random.RandomState()
+            g2.set_state(rng.get_state())
+            obs = np.abs(np.mean(a) - np.mean(b))
+            comb = np.concatenate([a, b])
+            diffs = []
+            for _ in range(10000):
+                g2.shuffle(comb)
+                diffs.append(np.abs(np.mean(comb[:len(a)]) - np.mean(comb[len(a):])))
+            ref_p = float(np.mean(np.array(diffs) >= obs))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if pre is not None:
+            p = mmx.permutation_test(a, b, index_rows=pre.index_rows(k))
+        else:
+            p = mmx.permutation_test(a, b, rng=rng)
+        torch.cuda.synchronize()
+        rec = {"pair": [i, j], "p": float(p), "ms": 1e3 * (time.perf_counter() - t0)}
+        if ref_p is not None:
+            rec["reference_p"] = ref_p
+            if pre is not None:
+                same_state = pre.stands_after(g2, k)
+            else:
+                g3 = np.random.RandomState()
+                g3.set_state(rng.get_state())
+                same_state = g2.randint(0, 1 << 30) == g3.randint(0, 1 << 30)
+            rec["same_p_and_generator_state"] = bool(ref_p == float(p) and same_state)
+        tests["per_query_n50000"].append(rec)
+    if pre is not None:
+        pre.commit(rng)                          # the generator continues behind the 21 prefetched tests
+    for i, j in pairs:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        p = mmx.permutation_test(rows[i]["_bootstrap_values"][:, 0], rows[j]["_bootstrap_values"][:, 0], rng=rng)
+        torch.cuda.synchronize()
+        tests["per_iteration_n2000"].append({"pair": [i, j], "p": float(p), "ms": 1e3 * (time.perf_counter() - t0)})
     torch.cuda.synchronize()
     t_tests = time.perf_counter() - t_tests
     out = {"workload": f"configs[4]: ColPali MaxSim {NQ} q x {ND} docs x {LD} patches, doc-sharded x{world}, {args.iterations}-iter "
                        f"bootstrap, {args.models} models, {len(tests['per_iteration_n2000'])} + {len(tests['per_query_n50000'])} permutation tests",
-           "n_gpus": world, "total_s": t_models + t_tests, "models_s": t_models, "tests_s": t_tests,
+           "n_gpus": world, "shuffles_prefetched_on_rank0_while_ranks_1_to_7_score": prefetch,
+           "total_s": t_models + t_tests, "models_s": t_models, "tests_s": t_tests,
            "per_model": phases, "peak_mem_GB_per_gpu": float(peak.item()),
            "tests": tests,
            "per_query_test_ms_mean": float(np.mean([r["ms"] for r in tests["per_query_n50000"]])) if tests["per_query_n50000"] else None,

@@ -255,16 +255,31 @@ def bootstrap_confidence_interval(data: np.ndarray, confidence: float = 0.95, rn
     return mean, lower, upper
 
 
-def permutation_test(data1: np.ndarray, data2: np.ndarray, n_permutations: int = 10000, rng=None) -> float:
+def skip_bootstrap_draws(drng: "ops.DeviceRng", n_units: int, n_iterations: int, n_ci_sets: int = len(KS)) -> None:
+    """Advance a device generator past the numpy draws of ONE run_retrieval_bootstrap call (n_iterations x choice(n, n), then
+    n_ci_sets x 10 000 x choice(values, n_iterations)) without keeping them — for ops.ShufflePrefetch, which replays the
+    permutation tests that FOLLOW the models' bootstraps in the stream while the models are still being scored."""
+    drng.randint(n_units, n_iterations * n_units)
+    drng.randint(n_iterations, n_ci_sets * N_BOOTSTRAP * n_iterations)
+
+
+def permutation_test(data1: np.ndarray, data2: np.ndarray, n_permutations: int = 10000, rng=None,
+                     index_rows: Optional[torch.Tensor] = None) -> float:
     """main.py:281-302. The cumulative in-place shuffles of ``combined`` are replayed on an index array with the
-    same numpy stream; the 2 x n_permutations means and |diff| run on the device in numpy's summation order."""
+    same numpy stream; the 2 x n_permutations means and |diff| run on the device in numpy's summation order.
+    ``index_rows`` (int32 CUDA [n_permutations, n], ops.ShufflePrefetch) supplies shuffles that were replayed ahead of
+    time from this very stream position; the generator is then left alone (ShufflePrefetch.commit moves it)."""
     dev = _device()
     data1, data2 = np.asarray(data1, dtype=np.float64), np.asarray(data2, dtype=np.float64)
     observed_diff = np.abs(np.mean(data1) - np.mean(data2))
     combined = np.concatenate([data1, data2])
     n1, n = len(data1), len(data1) + len(data2)
     r = _rng(rng)
-    if DEVICE_RNG and 2 <= n <= DEVICE_SHUFFLE_MAX_N and n_permutations >= 1:
+    if index_rows is not None:
+        if tuple(index_rows.shape) != (n_permutations, n):
+            raise ValueError("index_rows must be [n_permutations, len(data1) + len(data2)]")
+        perm_d = index_rows
+    elif DEVICE_RNG and 2 <= n <= DEVICE_SHUFFLE_MAX_N and n_permutations >= 1:
         # K6s: the shuffles themselves are replayed on the device from numpy's stream; numpy's generator is moved
         # past exactly the words they consumed
         drng = r if isinstance(r, ops.DeviceRng) else ops.DeviceRng(r, dev)

@@ -103,6 +103,8 @@ def maxsim_scores(q_tok: torch.Tensor, q_off: torch.Tensor, d_tok: torch.Tensor,
     nq, nd = q_off.numel() - 1, d_off.numel() - 1
     if out is None:
         out = torch.empty((nq, nd), dtype=torch.float32, device=q_tok.device)
+    if nq == 0 or nd == 0:
+        return out                                         # an empty shard (a rank that only helps with the statistics)
     need = ctypes.c_size_t()
     _lib.check(_lib.lib().mmx_maxsim_workspace_bytes(q_tok.shape[0], nd, d_tok.shape[0], ctypes.byref(need)))
     if need.value <= MAXSIM_WORKSPACE_LIMIT or nq <= 1:
@@ -680,3 +682,95 @@ class DeviceRng:
         host = self.state.cpu().numpy().view(np.uint32)
         st = self.source.get_state()
         self.source.set_state(("MT19937", host[:624].copy(), int(host[624]), st[3], st[4]))
+
+
+class ShufflePrefetch:
+    """The index rows of a KNOWN sequence of permutation tests, replayed ahead of time on a side stream.
+
+    numpy's stream does not depend on the data: which words a test's 10 000 shuffles consume is fixed by the generator
+    state alone. So the whole chain of tests — serial, ~0.07 ms per 50 000-element permutation on ONE SM — can run while
+    the GPU (or the other GPUs) still score the models whose vectors the tests will compare (BASELINE configs[4]: 21
+    per-query tests = 14.5 s of chain next to 8-10 s of MaxSim scoring). ``skip(drng)`` first advances the snapshot
+    past the draws that happen before the tests (the models' bootstrap draws, ``api.skip_bootstrap_draws``).
+
+        pre = ShufflePrefetch(rng, [(50000, 10000)] * 21, skip=...); pre.start()
+        ...                                                   # score the models (they advance `rng` themselves)
+        assert pre.starts_where(rng)                          # the dry run consumed exactly what the models did
+        p = api.permutation_test(a, b, index_rows=pre.index_rows(k))
+        pre.commit(rng)                                       # `rng` continues behind the last prefetched test
+    """
+
+    def __init__(self, source, tests: Sequence[Tuple[int, int]], device: Optional[torch.device] = None, skip=None):
+        import threading
+        self.tests = [(int(n), int(P)) for n, P in tests]
+        self.dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.drng = DeviceRng(source, self.dev)
+        self.drng._par_buffers(False)                      # jump tables are uploaded once, not from the worker thread
+        self.drng._par_buffers(True)
+        if skip is not None:
+            skip(self.drng)
+        torch.cuda.synchronize(self.dev)
+        self.start_state = self.drng.state.clone()
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.out = [None] * len(self.tests)
+        self.state_after = [None] * len(self.tests)         # generator state behind every test (625 words each)
+        self.ready = [threading.Event() for _ in self.tests]
+        self.error: Optional[BaseException] = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def start(self) -> "ShufflePrefetch":
+        self.thread.start()
+        return self
+
+    def _run(self) -> None:
+        try:
+            torch.cuda.set_device(self.dev)
+            with torch.cuda.stream(self.stream):
+                for k, (n, P) in enumerate(self.tests):
+                    rows = self.drng.shuffle_indices(n, P)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                    self.state_after[k] = self.drng.state.clone()
+                    self.out[k] = (rows, ev)
+                    self.ready[k].set()
+        except BaseException as exc:  # noqa: BLE001 - reported by the consumer
+            self.error = exc
+            for r in self.ready:
+                r.set()
+
+    @staticmethod
+    def _same_state(source, state: torch.Tensor) -> bool:
+        st = source.get_state()
+        host = state.cpu().numpy().view(np.uint32)
+        return bool(np.array_equal(np.asarray(st[1], dtype=np.uint32), host[:624]) and int(st[2]) == int(host[624]))
+
+    def starts_where(self, source) -> bool:
+        """True when `source` (numpy generator) stands exactly where the prefetched chain started."""
+        return self._same_state(source, self.start_state)
+
+    def stands_after(self, source, k: int) -> bool:
+        """True when `source` stands exactly where the chain stood after test k (for checks against numpy's own shuffles)."""
+        self.ready[k].wait()
+        self.stream.synchronize()
+        return self._same_state(source, self.state_after[k])
+
+    def index_rows(self, k: int) -> torch.Tensor:
+        """int32 CUDA [P, n] index rows of test k (blocks until its replay has been queued; the current stream waits
+        for it on the device)."""
+        self.ready[k].wait()
+        if self.error is not None:
+            raise self.error
+        rows, ev = self.out[k]
+        torch.cuda.current_stream().wait_event(ev)
+        rows.record_stream(torch.cuda.current_stream())
+        self.out[k] = None                                 # the caller owns them now
+        return rows
+
+    def commit(self, source) -> None:
+        """Move the numpy generator behind the last prefetched test."""
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+        self.stream.synchronize()
+        self.drng.source = source
+        self.drng.commit()

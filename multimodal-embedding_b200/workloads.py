@@ -71,12 +71,13 @@ def synth_colpali_shard(dev: torch.device, nq: int, nd: int, lq: int, ld: int, d
 
 
 def colpali_model(dev: torch.device, nq: int, nd: int, lq: int, ld: int, n_iterations: int, seed: int, sigma: float,
-                  rng, group=None, name: str = "model") -> Tuple[Optional[dict], np.ndarray, Dict[str, float]]:
+                  rng, group=None, name: str = "model", bounds=None) -> Tuple[Optional[dict], np.ndarray, Dict[str, float]]:
     """One ColPali 'model' of configs[4], doc-sharded over `group`: synthesize this rank's shard on the device, score +
     rank + bootstrap through ``api.run_retrieval_bootstrap``. Returns (row on rank 0 / None elsewhere, per-query Recall@1
     hit vector float64 [nq] (the same on every rank), phase times in ms)."""
     world, rank = _world(group)
-    bounds = sharded.shard_bounds(nd, world)
+    if bounds is None:
+        bounds = sharded.shard_bounds(nd, world)       # `bounds` may leave a rank without documents (it then only helps with the statistics)
     d0, d1 = bounds[rank]
     t = {}
     torch.cuda.synchronize(dev)
