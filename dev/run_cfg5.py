@@ -82,7 +82,7 @@ for m in range(args.models):
               f"CI [{row['R@1_lower']:.3f}, {row['R@1_upper']:.3f}]", flush=True)
 if world > 1:
     dist.barrier()
-torch.cuda.synchronize()
+torch.cuda.current_stream().synchronize()
 t_models = time.perf_counter() - t_all
 peak = torch.tensor([torch.cuda.max_memory_allocated() / 1e9], device=dev)
 if world > 1:
@@ -110,13 +110,13 @@ if rank == 0:
                 g2.shuffle(comb)
                 diffs.append(np.abs(np.mean(comb[:len(a)]) - np.mean(comb[len(a):])))
             ref_p = float(np.mean(np.array(diffs) >= obs))
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         t0 = time.perf_counter()
         if pre is not None:
             p = mmx.permutation_test(a, b, index_rows=pre.index_rows(k))
         else:
             p = mmx.permutation_test(a, b, rng=rng)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         rec = {"pair": [i, j], "p": float(p), "ms": 1e3 * (time.perf_counter() - t0)}
         if ref_p is not None:
             rec["reference_p"] = ref_p
@@ -131,12 +131,12 @@ if rank == 0:
     if pre is not None:
         pre.commit(rng)                          # the generator continues behind the 21 prefetched tests
     for i, j in pairs:
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         t0 = time.perf_counter()
         p = mmx.permutation_test(rows[i]["_bootstrap_values"][:, 0], rows[j]["_bootstrap_values"][:, 0], rng=rng)
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         tests["per_iteration_n2000"].append({"pair": [i, j], "p": float(p), "ms": 1e3 * (time.perf_counter() - t0)})
-    torch.cuda.synchronize()
+    torch.cuda.current_stream().synchronize()
     t_tests = time.perf_counter() - t_tests
     out = {"workload": f"configs[4]: ColPali MaxSim {NQ} q x {ND} docs x {LD} patches, doc-sharded x{world}, {args.iterations}-iter "
                        f"bootstrap, {args.models} models, {len(tests['per_iteration_n2000'])} + {len(tests['per_query_n50000'])} permutation tests",

@@ -604,9 +604,16 @@ class DeviceRng:
             cnt_d = torch.from_numpy(cnt).to(dev)
             _lib.check(_lib.lib().mmx_mt19937_par_set_bit_positions(polys.data_ptr(), pos_d.data_ptr(),
                                                                     cnt_d.data_ptr(), pos.shape[1]))
-            DeviceRng._tables[key] = (polys, torch.empty(need.value, dtype=torch.uint8, device=dev), pos_d, cnt_d,
+            DeviceRng._tables[key] = (polys, need.value, pos_d, cnt_d,
                                       mtjump.SEG_BLOCKS_LONG if long else mtjump.SEG_BLOCKS)
-        return DeviceRng._tables[key]
+        polys, need_bytes, pos_d, cnt_d, seg_blocks = DeviceRng._tables[key]
+        # the jump tables are shared per device; the scratch is per generator: two generators may draw at the same time
+        # on different streams (ShufflePrefetch next to a model's bootstrap draws)
+        if not hasattr(self, "_scratch"):
+            self._scratch = {}
+        if long not in self._scratch:
+            self._scratch[long] = torch.empty(need_bytes, dtype=torch.uint8, device=dev)
+        return polys, self._scratch[long], pos_d, cnt_d, seg_blocks
 
     def _table_for(self, raw_words: float):
         return self._par_buffers(long=raw_words >= self.LONG_MIN_WORDS)

@@ -80,10 +80,10 @@ def colpali_model(dev: torch.device, nq: int, nd: int, lq: int, ld: int, n_itera
         bounds = sharded.shard_bounds(nd, world)       # `bounds` may leave a rank without documents (it then only helps with the statistics)
     d0, d1 = bounds[rank]
     t = {}
-    torch.cuda.synchronize(dev)
+    torch.cuda.current_stream(dev).synchronize()   # not the device: a shuffle chain may be running on a side stream
     t0 = time.perf_counter()
     Q, D, q2d = synth_colpali_shard(dev, nq, nd, lq, ld, d0, d1, seed=seed, sigma=sigma)
-    torch.cuda.synchronize(dev)
+    torch.cuda.current_stream(dev).synchronize()   # not the device: a shuffle chain may be running on a side stream
     t["synthesize_ms"] = 1e3 * (time.perf_counter() - t0)
     qv = api.FlatMultiVector(Q, np.full(nq, lq))
     dv = api.FlatMultiVector(D, np.full(d1 - d0, ld))
@@ -92,7 +92,7 @@ def colpali_model(dev: torch.device, nq: int, nd: int, lq: int, ld: int, n_itera
     t0 = time.perf_counter()
     row = api.run_retrieval_bootstrap(qv, dv, q2d.cpu().numpy(), {"type": "colpali", "name": name}, n_iterations, rng=rng,
                                       group=group, timings=tm, shard_sizes=[e - b for b, e in bounds], keep=keep)
-    torch.cuda.synchronize(dev)
+    torch.cuda.current_stream(dev).synchronize()   # not the device: a shuffle chain may be running on a side stream
     t["score_rank_bootstrap_ms"] = 1e3 * (time.perf_counter() - t0)
     hits = (keep["ranks"].cnt_above < 1).to(torch.float64).cpu().numpy()     # per-query correct_r1 (main.py:342-356)
     if tm:
