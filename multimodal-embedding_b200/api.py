@@ -72,6 +72,15 @@ def _h2d(t: torch.Tensor, dev: torch.device, dtype=None) -> torch.Tensor:
     return t.to(dev, non_blocking=True)
 
 
+def _host_read(t: torch.Tensor) -> torch.Tensor:
+    """Device->host copy that first waits on the STREAM. A copy into pageable memory that has to wait for its stream
+    waits inside the driver and holds up the launches of every other host thread (ops.ShufflePrefetch's worker, which
+    replays the permutation tests' shuffles next to a sharded scoring pass, lost half its time to this); a stream wait
+    does not."""
+    torch.cuda.current_stream().synchronize()
+    return t.cpu()
+
+
 def _np_h2d(a: np.ndarray, dev: torch.device, dtype: torch.dtype) -> torch.Tensor:
     return _h2d(torch.from_numpy(np.ascontiguousarray(a)), dev, dtype)
 
@@ -691,6 +700,7 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     if world > 1 and shard_sizes is None:
         sizes = torch.zeros((world, 1), dtype=torch.int64, device=dev)
         dist.all_gather(list(sizes.unbind(0)), torch.tensor([n_local], dtype=torch.int64, device=dev), group=group)
+        torch.cuda.current_stream().synchronize()                        # (see _host_read)
         shard_sizes = sizes.view(-1).tolist()                            # one device->host read
     if world > 1:
         ends = np.cumsum(np.asarray(shard_sizes, dtype=np.int64))
@@ -710,7 +720,7 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         mine[:n_local] = torch.from_numpy(np.asarray(dv.lens, dtype=np.int32))
         all_l = torch.empty((world, n_max), dtype=torch.int32, device=dev)
         dist.all_gather(list(all_l.unbind(0)), mine.to(dev), group=group)
-        all_h = all_l.cpu().numpy()
+        all_h = _host_read(all_l).numpy()
         lens_all = np.concatenate([all_h[r, : e - b_] for r, (b_, e) in enumerate(bounds)])
         shard_flags = _pad_flags(lens_all)[g_base:g_base + n_local]
     # ---- the reference's numpy stream (the draws do not depend on the scores). K6p on a side stream regenerates it
@@ -816,6 +826,7 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         if rank != 0:
             return None
     marks.append(("stats_queued", time.perf_counter()))
+    torch.cuda.current_stream().synchronize()                            # (see _host_read)
     if DEVICE_RNG:
         drng.commit()                                                    # numpy's generator ends where the reference's would
     values_h = values.cpu().numpy()

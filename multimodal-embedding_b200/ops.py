@@ -5,8 +5,9 @@ the library or a CUDA device is missing — there is no eager/CPU fallback."""
 from __future__ import annotations
 
 import ctypes
+import time
 from dataclasses import dataclass
-from typing import Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -656,17 +657,22 @@ class DeviceRng:
                                                   mtjump.N_POLY, seg_blocks, scratch.data_ptr(),
                                                   scratch.numel(), _stream()))
 
+    @staticmethod
+    def shuffle_words_needed(n: int, n_shuffles: int) -> int:
+        """Raw words handed to the replay of n_shuffles shuffles of n items (mean + 8 sigma): step i accepts with
+        probability (i + 1) / 2^ceil(log2(i + 1))."""
+        i = np.arange(1, n, dtype=np.float64)
+        pacc = (i + 1.0) / np.exp2(np.ceil(np.log2(i + 1.0)))
+        mean = n_shuffles * float(np.sum(1.0 / pacc))
+        sigma = float(np.sqrt(n_shuffles * np.sum((1.0 - pacc) / pacc ** 2)))
+        return int(mean + 8.0 * sigma) + 2048
+
     def shuffle_indices(self, n: int, n_shuffles: int) -> torch.Tensor:
         """K6s. int32 CUDA [n_shuffles, n]: an index array after each of `n_shuffles` cumulative in-place
         ``shuffle`` calls (legacy RandomState.shuffle, main.py:296), consuming exactly the words numpy would."""
         h = _lib.lib()
         dev = self.state.device
-        # words a shuffle of n items needs: step i accepts with probability (i + 1) / 2^ceil(log2(i + 1))
-        i = np.arange(1, n, dtype=np.float64)
-        pacc = (i + 1.0) / np.exp2(np.ceil(np.log2(i + 1.0)))
-        mean = n_shuffles * float(np.sum(1.0 / pacc))
-        sigma = float(np.sqrt(n_shuffles * np.sum((1.0 - pacc) / pacc ** 2)))
-        n_words = int(mean + 8.0 * sigma) + 2048
+        n_words = self.shuffle_words_needed(n, n_shuffles)
         perm = torch.empty((n_shuffles, n), dtype=torch.int32, device=dev)
         info = torch.empty((2,), dtype=torch.int64, device=dev)
         while True:
@@ -676,6 +682,10 @@ class DeviceRng:
             ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
             _lib.check(h.mmx_perm_shuffle(words.data_ptr(), n_words, n, n_shuffles, perm.data_ptr(), info.data_ptr(),
                                           ws.data_ptr(), need.value, _stream()))
+            # wait on the stream first: a device->host copy into pageable memory that has to wait for its stream does so
+            # inside the driver, where it holds up the launches of every other host thread (ShufflePrefetch runs this
+            # on a worker thread next to the scoring thread)
+            torch.cuda.current_stream().synchronize()
             consumed = int(info[1].item())
             if consumed >= 0:
                 break
@@ -719,10 +729,25 @@ class ShufflePrefetch:
         torch.cuda.synchronize(self.dev)
         self.start_state = self.drng.state.clone()
         self.stream = torch.cuda.Stream(device=self.dev)
+        # cudaMalloc synchronises the whole device: an allocation made by the worker while the main stream sits in a
+        # collective (waiting for the other ranks' scoring) would stall the chain until that collective ends. So every
+        # buffer the chain will need is allocated once now, on its stream, and handed back to the caching allocator.
+        with torch.cuda.stream(self.stream):
+            warm = [torch.empty((P, n), dtype=torch.int32, device=self.dev) for n, P in self.tests]
+            warm.append(torch.empty(1024, dtype=torch.int64, device=self.dev))     # the small-block pool of this stream
+            for n, P in sorted(set(self.tests)):
+                n_words = self.drng.shuffle_words_needed(n, P)
+                need = ctypes.c_size_t()
+                _lib.check(_lib.lib().mmx_perm_shuffle_workspace_bytes(n, P, n_words, ctypes.byref(need)))
+                warm.append(torch.empty(n_words, dtype=torch.int32, device=self.dev))
+                warm.append(torch.empty(need.value, dtype=torch.uint8, device=self.dev))
+            del warm
+        torch.cuda.synchronize(self.dev)
         self.out = [None] * len(self.tests)
         self.state_after = [None] * len(self.tests)         # generator state behind every test (625 words each)
         self.ready = [threading.Event() for _ in self.tests]
         self.error: Optional[BaseException] = None
+        self.trace: List[Tuple[int, float, float]] = []      # (test, host time.perf_counter() at start, at end)
         self.thread = threading.Thread(target=self._run, daemon=True)
 
     def start(self) -> "ShufflePrefetch":
@@ -734,7 +759,9 @@ class ShufflePrefetch:
             torch.cuda.set_device(self.dev)
             with torch.cuda.stream(self.stream):
                 for k, (n, P) in enumerate(self.tests):
+                    t0 = time.perf_counter()
                     rows = self.drng.shuffle_indices(n, P)
+                    self.trace.append((k, t0, time.perf_counter()))
                     ev = torch.cuda.Event()
                     ev.record(self.stream)
                     self.state_after[k] = self.drng.state.clone()
