@@ -153,19 +153,24 @@ int mmx_place_bit_columns(const uint32_t* gathered, int n_shards, int64_t nq, in
  * mmx_dense_rank_lists: the COUNT pass of mmx_dense_rank (thr = merged thresholds, input) with cnt_above int32 [nq]
  *                   (exact strict-greater count) and, instead of bits, list_i int32 [nq, cap] global column ids of the
  *                   first hits to arrive + list_n int32 [nq] cursor (valid entries = min(list_n, cap)). Both zeroed here.
- * mmx_lists_to_units: per-shard lists [n_shards, nq, cap] + cursors [n_shards, nq] (one all-gather when sharded)
- *                   -> list_t [L, nq] transposed unit lists (col2unit nullable = identity), avail int32 [nq].
- * mmx_boot_counts_lists: K3 on those lists. (iteration, query) pairs whose truncated list ran out below a multiplicity
- *                   of 10 are left OUT of `correct` and reported as int32 pairs in unres [unres_cap, 2]; *unres_n counts
- *                   them all (call again with more room if it exceeds unres_cap). The caller recounts them from the
- *                   scores (api._resolve_unlisted); with cap = 64 the probability of one is ~1e-17 per pair. */
+ * mmx_boot_counts_lists: K3 straight from the per-shard lists list_i [n_shards, nq, cap] + cursors list_n [n_shards, nq]
+ *                   (one all-gather when sharded; n_shards = 1 otherwise). Query q's list = its shards' lists in shard
+ *                   order, cut at L <= cap entries (col2unit nullable = identity). One warp per query, the
+ *                   iterations across the lanes (the multiplicities are transposed into `workspace` first, 128
+ *                   iterations per 128-byte row): a list entry costs one coalesced load for 128 iterations.
+ *                   (iteration, query) pairs whose truncated list ran out below a multiplicity of 10 are left OUT of
+ *                   `correct` and reported as int32 pairs in unres [unres_cap, 2] (any order); *unres_n counts them all
+ *                   (call again with more room if it exceeds unres_cap). The caller recounts them from the scores
+ *                   (ops.dense_unlisted_resolver); with cap = 64 the probability of one is ~1e-17 per pair.
+ *                   workspace: mmx_boot_counts_lists_workspace_bytes(B, n_units) device bytes, 16-byte aligned. */
 int mmx_dense_rank_lists(const void* Q, int64_t nq, const void* G, int64_t ng, int d, int64_t g_base, const float* thr,
                          int32_t* cnt_above, int32_t* list_i, int32_t* list_n, int cap, cudaStream_t stream);
-int mmx_lists_to_units(const int32_t* list_i, const int32_t* list_n, int n_shards, int64_t nq, int cap,
-                       const int32_t* col2unit, int L, int32_t* list_t, int32_t* avail, cudaStream_t stream);
-int mmx_boot_counts_lists(const int32_t* list_t, int L, const int32_t* cnt_above, const int32_t* q_unit,
-                          const uint8_t* mult, int B, int64_t n_units, int64_t nq, int32_t* correct, int32_t* q_hits1,
-                          int32_t* unres, int32_t* unres_n, int unres_cap, cudaStream_t stream);
+int mmx_boot_counts_lists_workspace_bytes(int B, int64_t n_units, size_t* bytes);
+int mmx_boot_counts_lists(const int32_t* list_i, const int32_t* list_n, int n_shards, int64_t nq, int cap,
+                          const int32_t* col2unit, int L, const int32_t* cnt_above, const int32_t* q_unit,
+                          const uint8_t* mult, int B, int64_t n_units, int32_t* correct, int32_t* q_hits1,
+                          int32_t* unres, int32_t* unres_n, int unres_cap, void* workspace, size_t workspace_bytes,
+                          cudaStream_t stream);
 
 /* K4  CI resample means — replaces the 10 000 x (np.random.choice(data, n) ; np.mean) loop of main.py:268-270.
  * idx int32 [R, n] is the reference's index stream (RandomState.randint(0, n, (R, n)) == R x choice);
@@ -206,6 +211,14 @@ int mmx_mt19937_par_set_bit_positions(const uint32_t* polys, const uint16_t* bit
 int mmx_mt19937_par_set_slack(double rel, double blocks);
 int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t count, int32_t* out, const uint32_t* polys,
                             int n_poly, int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream);
+/* The same request, of which only the values [win_begin, win_begin + win_count) are stored (out int32 [win_count],
+ * nullable when win_count == 0): the generator advances by all `count` values, but segments that hold nothing of the
+ * window skip their write pass. A rank that bootstraps iterations [b0, b1) of a sharded run (main.py:586-588: one
+ * np.random.choice(n, n) per iteration) draws the whole stream's positions and keeps its own rows only; win_count == 0
+ * skips a request (ops.ShufflePrefetch runs ahead of the models' draws that way). */
+int mmx_mt19937_randint_par_window(uint32_t* state, uint32_t high, int64_t count, int32_t* out, int64_t win_begin,
+                                   int64_t win_count, const uint32_t* polys, int n_poly, int seg_blocks, void* scratch,
+                                   size_t scratch_bytes, cudaStream_t stream);
 
 /* The next `count` raw 32-bit outputs of the stream (genrand_int32), produced like K6p; out nullable = only advance
  * the generator state by `count` words. */

@@ -127,14 +127,12 @@ _SIGNATURES = {
         _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int64,   # Q, nq, G, ng, d, g_base
         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,  # thr, cnt_above, list_i, list_n, cap, stream
     ]),
-    "mmx_lists_to_units": (_c.c_int, [
-        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int,     # list_i, list_n, n_shards, nq, cap
-        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,  # col2unit, L, list_t, avail, stream
-    ]),
+    "mmx_boot_counts_lists_workspace_bytes": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_size_t)]),
     "mmx_boot_counts_lists": (_c.c_int, [
-        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,  # list_t, L, cnt_above, q_unit, mult
-        _c.c_int, _c.c_int64, _c.c_int64, _c.c_void_p, _c.c_void_p,    # B, n_units, nq, correct, q_hits1
-        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,               # unres, unres_n, unres_cap, stream
+        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64, _c.c_int,     # list_i, list_n, n_shards, nq, cap
+        _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,              # col2unit, L, cnt_above, q_unit
+        _c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p,  # mult, B, n_units, correct, q_hits1
+        _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p,  # unres, unres_n, unres_cap, workspace, bytes, stream
     ]),
     "mmx_ci_means": (_c.c_int, [
         _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,   # data, n, idx, R, means, stream
@@ -148,6 +146,10 @@ _SIGNATURES = {
     "mmx_mt19937_par_set_slack": (_c.c_int, [_c.c_double, _c.c_double]),
     "mmx_mt19937_randint_par": (_c.c_int, [
         _c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p,            # state, high, count, out
+        _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p,   # polys, n_poly, seg_blocks, scratch, bytes, stream
+    ]),
+    "mmx_mt19937_randint_par_window": (_c.c_int, [
+        _c.c_void_p, _c.c_uint32, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int64,   # state, high, count, out, win_begin, win_count
         _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p,   # polys, n_poly, seg_blocks, scratch, bytes, stream
     ]),
     "mmx_mt19937_raw_par": (_c.c_int, [

@@ -268,8 +268,8 @@ def skip_bootstrap_draws(drng: "ops.DeviceRng", n_units: int, n_iterations: int,
     """Advance a device generator past the numpy draws of ONE run_retrieval_bootstrap call (n_iterations x choice(n, n), then
     n_ci_sets x 10 000 x choice(values, n_iterations)) without keeping them — for ops.ShufflePrefetch, which replays the
     permutation tests that FOLLOW the models' bootstraps in the stream while the models are still being scored."""
-    drng.randint(n_units, n_iterations * n_units)
-    drng.randint(n_iterations, n_ci_sets * N_BOOTSTRAP * n_iterations)
+    drng.randint(n_units, n_iterations * n_units, window=(0, 0))
+    drng.randint(n_iterations, n_ci_sets * N_BOOTSTRAP * n_iterations, window=(0, 0))
 
 
 def permutation_test(data1: np.ndarray, data2: np.ndarray, n_permutations: int = 10000, rng=None,
@@ -684,6 +684,13 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
     from . import sharded
     dev = _device()
     marks = [("enter", time.perf_counter())]
+    dev_marks: List[Tuple[str, Any]] = []                # (phase, CUDA event) on the main stream, only when timings are asked for
+
+    def mark(name: str, stream=None) -> None:
+        if timings is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream if stream is not None else torch.cuda.current_stream())
+            dev_marks.append((name, e))
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     if world > 1 and group is None:
@@ -739,13 +746,25 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
                 dist.broadcast(drng.state, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
             side = _aux_stream(dev, "rng")
             side.wait_stream(torch.cuda.current_stream())
+            rng_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)] if timings is not None else None
             with torch.cuda.stream(side):
-                sample_indices = drng.randint(n_docs, n_iterations * n_docs).view(n_iterations, n_docs)  # main.py:588
+                if rng_ev:
+                    rng_ev[0].record(side)
+                # main.py:588. With the statistics split over the ranks, each keeps the rows of ITS block of iterations
+                # (the stream is replayed in full everywhere — its positions depend on every rejection before them —
+                # but segments outside the block skip their write pass)
+                b0, b1 = sharded.stats_block(n_iterations, group) if split_stats else (0, n_iterations)
+                sample_indices = drng.randint(n_docs, n_iterations * n_docs, window=(b0 * n_docs, (b1 - b0) * n_docs))
+                sample_indices = (sample_indices.view(b1 - b0, n_docs) if sample_indices is not None
+                                  else torch.empty((0, n_docs), dtype=torch.int32, device=dev))
                 ci_idx = drng.randint(n_iterations, len(KS) * N_BOOTSTRAP * n_iterations).view(
                     len(KS), N_BOOTSTRAP, n_iterations)                   # main.py:269, the three CIs' draws in stream order
                 rng_done = torch.cuda.Event()
                 rng_done.record(side)
+                if rng_ev:
+                    rng_ev[1].record(side)
     marks.append(("rng_queued", time.perf_counter()))
+    mark("start")
     gt_off = torch.arange(nq + 1, dtype=torch.int32, device=dev)
     gt_idx = _np_h2d(q2d, dev, torch.int32)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -778,7 +797,9 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         ci_idx = _np_h2d(r.randint(0, n_iterations, size=(len(KS), N_BOOTSTRAP, n_iterations)).astype(np.int32), dev,
                          torch.int32)
     marks.append(("score_queued", time.perf_counter()))
+    mark("first_pass")
     thr = sharded.merge_thresholds(local.thr, group)
+    mark("thresholds_all_reduce")
     if fused_rank:
         pass                                             # thresholds, counts and bit rows are already there
     elif colpali:
@@ -788,7 +809,9 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         recount = ops.dense_unlisted_resolver(Q, G, thr, None, g_base)        # this shard's share of an exact recount
     else:
         local = ops.dense_rank(Q, G, gt_off, gt_idx, g_base=g_base, thr=thr)
+    mark("second_pass")
     ranks = sharded.merge_ranks(local, bounds, group)
+    mark("merge_all_gather")
     ranks.q_unit = gt_idx
     if keep is not None:
         keep["ranks"] = ranks
@@ -818,11 +841,13 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         means = ops.ci_means_batched(values.t().contiguous(), ci_idx)                                # three CIs, one launch
     else:
         torch.cuda.current_stream().wait_event(rng_done)
+        mark("wait_for_numpy_stream")
         for t in (sample_indices, ci_idx):
             t.record_stream(torch.cuda.current_stream())
         k3_stats = {}
         boot_fn = sharded.list_boot_fn(recount, group, k3_stats) if list_mode else None
-        values, means = sharded.bootstrap_stats(ranks, sample_indices, ci_idx, gt_idx, n_docs, group, boot_fn=boot_fn)
+        values, means = sharded.bootstrap_stats(ranks, sample_indices, ci_idx, gt_idx, n_docs, group, boot_fn=boot_fn,
+                                                mark=mark if timings is not None else None, n_iterations=n_iterations)
         if rank != 0:
             return None
     marks.append(("stats_queued", time.perf_counter()))
@@ -847,6 +872,10 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
                              "unresolved_pairs": k3_stats.get("unresolved_pairs", 0)}
     if timings is not None:
         timings["score_ms"] = ev[0].elapsed_time(ev[1])
+        # device time between consecutive phase marks on the main stream (this rank), and the numpy-stream replay on its own
+        timings["device_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(dev_marks[:-1], dev_marks[1:])}
+        if DEVICE_RNG and (rank == 0 or split_stats) and rng_ev:
+            timings["device_ms"]["numpy_stream_replay (side stream)"] = rng_ev[0].elapsed_time(rng_ev[1])
         marks.append(("return", time.perf_counter()))
         timings["wall_ms"] = {k: 1e3 * (t - marks[0][1]) for k, t in marks[1:]}     # host checkpoints since entry
     return out

@@ -42,7 +42,8 @@ __device__ __forceinline__ uint32_t temper(uint32_t y) {
 
 __global__ void __launch_bounds__(THREADS, 16)
 mt19937_randint_kernel(uint32_t* __restrict__ state, uint32_t rng, uint32_t mask, long long count,
-                       int32_t* __restrict__ out, const unsigned long long* __restrict__ seg_cnt, int n_seg) {
+                       int32_t* __restrict__ out, const unsigned long long* __restrict__ seg_cnt, int n_seg,
+                       long long win_lo, long long win_hi) {   // only values [win_lo, win_hi) of the request are stored
     __shared__ uint32_t key[2][N];
     __shared__ int round_cnt[32];
     __shared__ int new_pos_s;
@@ -110,7 +111,8 @@ mt19937_randint_kernel(uint32_t* __restrict__ state, uint32_t rng, uint32_t mask
             if (r < ROUNDS && ((m[j] >> lane) & 1u)) {
                 const int off = base + __popc(m[j] & lt);
                 if ((long long)off < need) {
-                    if (out != nullptr) out[produced + off] = (int32_t)v[j];
+                    const long long idx = produced + off;
+                    if (out != nullptr && idx >= win_lo && idx < win_hi) out[idx] = (int32_t)v[j];
                     if (last_block && (long long)off == need - 1) new_pos_s = r * 32 + lane + 1;
                 }
             }
@@ -149,7 +151,8 @@ extern "C" int mmx_mt19937_randint(uint32_t* state, uint32_t high, int64_t count
     mask |= mask >> 4;
     mask |= mask >> 8;
     mask |= mask >> 16;
-    rng::mt19937_randint_kernel<<<1, rng::THREADS, 0, stream>>>(state, r, mask, (long long)count, out, nullptr, 0);
+    rng::mt19937_randint_kernel<<<1, rng::THREADS, 0, stream>>>(state, r, mask, (long long)count, out, nullptr, 0, 0,
+                                                                (long long)count);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -187,8 +190,9 @@ struct ParParams {
     uint32_t* seg_states;         // [n_seg][624]
     unsigned long long* seg_cnt;  // [n_seg]
     uint32_t* state_out;          // [625] key + pos where the request ends
-    int32_t* out;
+    int32_t* out;                 // nullable (only advance the state); indexed by the value's position in this launch
     long long count;
+    long long win_lo, win_hi;     // only values [win_lo, win_hi) of this launch are stored (a rank's block of the stream)
     int n_seg, seg_blocks;
     uint32_t rng, mask;
 };
@@ -334,6 +338,13 @@ mt_par_write_kernel(const ParParams p) {
     const long long base = (long long)base_s;
     const bool shortfall = (long long)total_s < p.count;
     if (base >= p.count) return;  // the request ends in an earlier segment
+    {
+        // nothing to store from this segment (no output, or outside the window) and the request does not end in it:
+        // the count pass already told everybody where the later segments start
+        const long long seg_end = base + (long long)p.seg_cnt[k];
+        const bool terminal = seg_end >= p.count || (shortfall && k == p.n_seg - 1);
+        if (!terminal && (p.out == nullptr || seg_end <= p.win_lo || base >= p.win_hi)) return;
+    }
     long long produced = base;    // global index of the next value this CTA emits
     int cur = 0;
     int pos = (k == 0) ? (int)p.state[N] : N;
@@ -381,7 +392,8 @@ mt_par_write_kernel(const ParParams p) {
             if (r < ROUNDS && ((m[j] >> lane) & 1u)) {
                 const int off = bs + __popc(m[j] & lt);
                 if ((long long)off < need) {
-                    if (p.out != nullptr) p.out[produced + off] = (int32_t)v[j];
+                    const long long idx = produced + off;
+                    if (p.out != nullptr && idx >= p.win_lo && idx < p.win_hi) p.out[idx] = (int32_t)v[j];
                     if (last_block && (long long)off == need - 1) stop_pos_s = r * 32 + lane + 1;
                 }
             }
@@ -465,8 +477,10 @@ extern "C" int mmx_mt19937_par_set_bit_positions(const uint32_t* polys, const ui
 }
 
 // rng_incl = inclusive maximum of the masked-rejection draw (0xffffffff: every raw word is a value)
-static int par_generate(uint32_t* state, uint32_t rng_incl, int64_t count, int32_t* out, const uint32_t* polys,
-                        int n_poly, int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+// out holds the values [win_begin, win_begin + win_count) of the request (the generator advances by all `count`)
+static int par_generate(uint32_t* state, uint32_t rng_incl, int64_t count, int32_t* out, int64_t win_begin,
+                        int64_t win_count, const uint32_t* polys, int n_poly, int seg_blocks, void* scratch,
+                        size_t scratch_bytes, cudaStream_t stream) {
     using namespace mmx::rng;
     size_t need = 0;
     mmx_mt19937_par_scratch_bytes(n_poly, &need);
@@ -508,7 +522,10 @@ static int par_generate(uint32_t* state, uint32_t rng_incl, int64_t count, int32
         const int64_t c = (count - done < cap_count) ? (count - done) : cap_count;
         int n_seg = (int)(budget_words(p.rng, (double)c) / per_seg) + 1;
         if (n_seg > n_poly + 1) n_seg = n_poly + 1;
-        p.out = out != nullptr ? out + done : nullptr;
+        p.win_lo = std::max<int64_t>(win_begin - done, 0);
+        p.win_hi = std::min<int64_t>(win_begin + win_count - done, c);
+        // p.out[i] = value i of this launch: value done + i of the request = out[done + i - win_begin]
+        p.out = (out != nullptr && p.win_hi > p.win_lo) ? out + (done - win_begin) : nullptr;
         p.count = c;
         p.n_seg = n_seg;
         mt_par_expand_kernel<<<1, PTHREADS, 0, stream>>>(p);
@@ -516,7 +533,8 @@ static int par_generate(uint32_t* state, uint32_t rng_incl, int64_t count, int32
         mt_par_write_kernel<<<n_seg, PTHREADS, 0, stream>>>(p);
         MMX_CHECK_CUDA(cudaGetLastError());
         MMX_CHECK_CUDA(cudaMemcpyAsync(state, p.state_out, 625 * 4, cudaMemcpyDeviceToDevice, stream));
-        mt19937_randint_kernel<<<1, THREADS, 0, stream>>>(state, p.rng, p.mask, (long long)c, p.out, p.seg_cnt, n_seg);
+        mt19937_randint_kernel<<<1, THREADS, 0, stream>>>(state, p.rng, p.mask, (long long)c, p.out, p.seg_cnt, n_seg,
+                                                          p.win_lo, p.win_hi);
         MMX_CHECK_CUDA(cudaGetLastError());
         done += c;
     }
@@ -531,7 +549,24 @@ extern "C" int mmx_mt19937_randint_par(uint32_t* state, uint32_t high, int64_t c
     MMX_REQUIRE(high >= 1 && high <= 0x7fffffffu, "high must be in [1, 2^31)");
     MMX_REQUIRE(count >= 0 && n_poly >= 1 && seg_blocks >= 1, "bad argument");
     if (count == 0 || high == 1) return mmx_mt19937_randint(state, high, count, out, stream);
-    return par_generate(state, high - 1, count, out, polys, n_poly, seg_blocks, scratch, scratch_bytes, stream);
+    return par_generate(state, high - 1, count, out, 0, count, polys, n_poly, seg_blocks, scratch, scratch_bytes, stream);
+}
+
+extern "C" int mmx_mt19937_randint_par_window(uint32_t* state, uint32_t high, int64_t count, int32_t* out,
+                                              int64_t win_begin, int64_t win_count, const uint32_t* polys, int n_poly,
+                                              int seg_blocks, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    MMX_REQUIRE(state != nullptr && polys != nullptr && scratch != nullptr, "NULL argument");
+    MMX_REQUIRE(high >= 1 && high <= 0x7fffffffu, "high must be in [1, 2^31)");
+    MMX_REQUIRE(count >= 0 && n_poly >= 1 && seg_blocks >= 1, "bad argument");
+    MMX_REQUIRE(win_begin >= 0 && win_count >= 0 && win_begin + win_count <= count, "window outside the request");
+    MMX_REQUIRE(out != nullptr || win_count == 0, "out == NULL with a non-empty window");
+    if (count == 0) return 0;
+    if (high == 1) {  // numpy draws nothing for a single-value range
+        if (win_count > 0) MMX_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)win_count * sizeof(int32_t), stream));
+        return 0;
+    }
+    return par_generate(state, high - 1, count, win_count > 0 ? out : nullptr, win_begin, win_count, polys, n_poly,
+                        seg_blocks, scratch, scratch_bytes, stream);
 }
 
 extern "C" int mmx_mt19937_raw_par(uint32_t* state, int64_t count, uint32_t* out, const uint32_t* polys, int n_poly,
@@ -539,6 +574,6 @@ extern "C" int mmx_mt19937_raw_par(uint32_t* state, int64_t count, uint32_t* out
     MMX_REQUIRE(state != nullptr && polys != nullptr && scratch != nullptr, "NULL argument");
     MMX_REQUIRE(count >= 0 && n_poly >= 1 && seg_blocks >= 1, "bad argument");
     if (count == 0) return 0;
-    return par_generate(state, 0xffffffffu, count, reinterpret_cast<int32_t*>(out), polys, n_poly, seg_blocks, scratch,
-                        scratch_bytes, stream);
+    return par_generate(state, 0xffffffffu, count, reinterpret_cast<int32_t*>(out), 0, count, polys, n_poly, seg_blocks,
+                        scratch, scratch_bytes, stream);
 }

@@ -62,25 +62,137 @@ __global__ void above_lists_kernel(const uint32_t* __restrict__ bits, long long 
     }
 }
 
-// LIST mode (K1 mmx_dense_rank_lists): per-shard column lists [n_shards, nq, cap] + cursors [n_shards, nq] ->
-// list_t[i * nq + q] = unit of the i-th entry of query q's concatenated lists (shard order), i < L; total[q] = number
-// of entries available (sum of min(cursor, cap) over shards, unclamped by L).
-__global__ void lists_to_units_kernel(const int32_t* __restrict__ list_i, const int32_t* __restrict__ list_n,
-                                      int n_shards, long long nq, int cap, const int32_t* __restrict__ col2unit, int L,
-                                      int32_t* __restrict__ list_t, int32_t* __restrict__ avail) {
-    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    int pos = 0, tot = 0;
-    for (int s = 0; s < n_shards; ++s) {
-        const int n = min(list_n[(long long)s * nq + q], cap);
-        tot += n;
-        const int32_t* src = list_i + ((long long)s * nq + q) * cap;
-        for (int i = 0; i < n && pos < L; ++i, ++pos) {
-            const int32_t col = src[i];
-            list_t[(long long)pos * nq + q] = col2unit != nullptr ? col2unit[col] : col;
+// LIST mode (K1 mmx_dense_rank_lists): per-shard column lists [n_shards, nq, cap] + cursors [n_shards, nq]. Query q's
+// list is the concatenation of its shards' lists in shard order, cut at L entries.
+//
+// The walk is laid out the other way round from boot_counts_kernel: ONE WARP PER QUERY, the bootstrap iterations across
+// the lanes. The multiplicities are transposed first (mult_t[chunk][unit][128] uint8: the 128 iterations of a chunk of one
+// unit are one 128-byte line), so a list entry costs the warp ONE coalesced 128-byte load that serves 128 iterations, the
+// lists are read once per chunk instead of once per iteration, and up to LOOKAHEAD loads are in flight per warp (the
+// addresses come from the list, not from the running sums). With one thread per (iteration, query) a 10^6-query,
+// 125-iteration block re-read the 256 MB list array 125 times with one random byte gather per entry: 54 ms; this
+// layout: see profiles/.
+constexpr int CHUNK_B = 128;     // iterations per chunk = bytes per mult_t row
+constexpr int LOOKAHEAD = 8;
+
+// mult [B, n_units] -> mult_t [n_chunks][n_units][128] (iterations beyond B: 0 = "query not drawn", which the walk skips)
+__global__ void __launch_bounds__(256)
+transpose_mult_kernel(const uint8_t* __restrict__ mult, int B, long long n_units, uint8_t* __restrict__ mult_t) {
+    __shared__ uint8_t tile[CHUNK_B][CHUNK_B + 4];
+    const int chunk = blockIdx.y;
+    const long long u0 = (long long)blockIdx.x * CHUNK_B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int it = warp; it < CHUNK_B; it += 8) {
+        const int b = chunk * CHUNK_B + it;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long u = u0 + k * 32 + lane;
+            tile[it][k * 32 + lane] = (b < B && u < n_units) ? mult[(long long)b * n_units + u] : (uint8_t)0;
         }
     }
-    avail[q] = tot;
+    __syncthreads();
+    uint32_t* dst = reinterpret_cast<uint32_t*>(mult_t + ((long long)chunk * n_units + u0) * CHUNK_B);
+    for (int u = warp; u < CHUNK_B && u0 + u < n_units; u += 8) {
+        const uint32_t v = (uint32_t)tile[4 * lane][u] | ((uint32_t)tile[4 * lane + 1][u] << 8) |
+                           ((uint32_t)tile[4 * lane + 2][u] << 16) | ((uint32_t)tile[4 * lane + 3][u] << 24);
+        dst[u * 32 + lane] = v;
+    }
+}
+
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t a, uint32_t b) { return __vcmpgeu4(a, b); }  // 0xff per byte a >= b
+
+__global__ void __launch_bounds__(256)
+boot_counts_lists_kernel(const int32_t* __restrict__ list_i, const int32_t* __restrict__ list_n, int n_shards,
+                         long long nq, int cap, const int32_t* __restrict__ col2unit, int L,
+                         const int32_t* __restrict__ cnt_above, const int32_t* __restrict__ q_unit,
+                         const uint8_t* __restrict__ mult_t, int B, long long n_units, int32_t* __restrict__ correct,
+                         int32_t* __restrict__ q_hits1, int32_t* __restrict__ unres, int32_t* __restrict__ unres_n,
+                         int unres_cap) {
+    __shared__ int red[8][3][CHUNK_B];
+    const int chunk = blockIdx.y, b0 = chunk * CHUNK_B;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t* mt = reinterpret_cast<const uint32_t*>(mult_t + (long long)chunk * n_units * CHUNK_B);
+    int acc[3][4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[k][j] = 0;
+    const long long n_warps = (long long)gridDim.x * 8;
+    for (long long q = (long long)blockIdx.x * 8 + warp; q < nq; q += n_warps) {
+        const long long uq = q_unit != nullptr ? q_unit[q] : q;
+        const uint32_t mq4 = mt[uq * 32 + lane];                       // this lane's four iterations' copies of the query
+        const uint32_t drawn = ~bytes_ge(0u, mq4);                     // 0xff where the query was drawn (mq > 0)
+        if (__ballot_sync(0xffffffffu, drawn != 0u) == 0u) continue;
+        const int cnt = cnt_above[q];
+        const int len = min(cnt, L);
+        uint32_t c4 = 0;                                               // four running sums, saturating bytes
+        bool done = __ballot_sync(0xffffffffu, (drawn & ~bytes_ge(c4, 0x0a0a0a0au)) != 0u) == 0u;
+        int pos = 0;
+        for (int s = 0; s < n_shards && pos < len && !done; ++s) {
+            const int take = min(min(list_n[(long long)s * nq + q], cap), len - pos);
+            const int32_t* src = list_i + ((long long)s * nq + q) * cap;
+            for (int base = 0; base < take && !done; base += 32) {
+                const int m = min(32, take - base);
+                long long unit = 0;
+                if (lane < m) {
+                    const int32_t col = src[base + lane];
+                    unit = col2unit != nullptr ? col2unit[col] : col;
+                }
+                for (int i0 = 0; i0 < m && !done; i0 += LOOKAHEAD) {
+                    uint32_t v[LOOKAHEAD];
+#pragma unroll
+                    for (int j = 0; j < LOOKAHEAD; ++j) {
+                        const long long u = __shfl_sync(0xffffffffu, unit, (i0 + j) & 31);
+                        v[j] = (i0 + j < m) ? mt[u * 32 + lane] : 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < LOOKAHEAD; ++j) c4 = __vaddus4(c4, v[j]);
+                    // every drawn iteration of every lane at 10 or more: the rest of the list cannot change anything
+                    done = __ballot_sync(0xffffffffu, (drawn & ~bytes_ge(c4, 0x0a0a0a0au)) != 0u) == 0u;
+                }
+            }
+            pos += take;
+        }
+        int h1_sum = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int mq = (int)((mq4 >> (8 * j)) & 0xffu);
+            const int c = (int)((c4 >> (8 * j)) & 0xffu);
+            if (mq == 0) continue;
+            if (c < 10 && cnt > L) {
+                // the truncated list ran out before saturating: leave this (iteration, query) out of the sums and report it;
+                // the caller recounts it exactly from the scores
+                const int slot = atomicAdd(unres_n, 1);
+                if (slot < unres_cap) {
+                    unres[2 * slot] = b0 + 4 * lane + j;
+                    unres[2 * slot + 1] = (int32_t)q;
+                }
+                continue;
+            }
+            const int h1 = min(mq, max(0, 1 - c));
+            h1_sum += h1;
+            acc[0][j] += h1;
+            acc[1][j] += min(mq, max(0, 5 - c));
+            acc[2][j] += min(mq, max(0, 10 - c));
+        }
+        if (q_hits1 != nullptr) {                                      // per-query R@1 hits over all iterations
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) h1_sum += __shfl_xor_sync(0xffffffffu, h1_sum, o);
+            if (lane == 0 && h1_sum > 0) atomicAdd(q_hits1 + q, h1_sum);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) red[warp][k][4 * lane + j] = acc[k][j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * CHUNK_B; i += blockDim.x) {
+        const int k = i / CHUNK_B, it = i % CHUNK_B;
+        int sum = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w][k][it];
+        if (b0 + it < B && sum != 0) atomicAdd(correct + (long long)(b0 + it) * 3 + k, sum);
+    }
 }
 
 // One block per bootstrap iteration b. mult[b,:] (uint8, saturated) sits in shared memory when it fits.
@@ -88,8 +200,7 @@ __global__ void __launch_bounds__(256)
 boot_counts_kernel(const int32_t* __restrict__ list_t, int L, const int32_t* __restrict__ cnt_above,
                    const uint32_t* __restrict__ bits, long long wpr, const int32_t* __restrict__ col2unit,
                    const int32_t* __restrict__ q_unit, const uint8_t* __restrict__ mult, long long n_units,
-                   long long nq, int mult_in_smem, int32_t* __restrict__ correct, int32_t* __restrict__ q_hits1,
-                   int32_t* __restrict__ unres, int32_t* __restrict__ unres_n, int unres_cap) {
+                   long long nq, int mult_in_smem, int32_t* __restrict__ correct, int32_t* __restrict__ q_hits1) {
     extern __shared__ uint8_t sm_mult[];
     __shared__ int red[3][8];
     const int b = blockIdx.x;
@@ -107,16 +218,6 @@ boot_counts_kernel(const int32_t* __restrict__ list_t, int L, const int32_t* __r
         const int len = min(cnt, L);
         int c = 0;
         for (int i = 0; i < len && c < 10; ++i) c += mrow[list_t[(long long)i * nq + q]];
-        if (c < 10 && cnt > L && bits == nullptr) {
-            // LIST mode: the truncated list ran out before saturating and there is no bitmask to fall back to: leave
-            // this (iteration, query) out of the sums and report it; the caller recounts it exactly from the scores
-            const int slot = atomicAdd(unres_n, 1);
-            if (slot < unres_cap) {
-                unres[2 * slot] = b;
-                unres[2 * slot + 1] = (int32_t)q;
-            }
-            continue;
-        }
         if (c < 10 && cnt > L) {
             // truncated list ran out before saturating: exact walk over the bitmask row (rare)
             c = 0;
@@ -458,38 +559,48 @@ extern "C" int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_
     if (smem > 48 * 1024 && first_use_on_device(&boot_tag))
         MMX_CHECK_CUDA(cudaFuncSetAttribute(boot_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
     boot_counts_kernel<<<B, 256, smem, stream>>>(list_t, L, cnt_above, above_bits, words_per_row, col2unit, q_unit, mult,
-                                                 n_units, nq, in_smem, correct, q_hits1, nullptr, nullptr, 0);
+                                                 n_units, nq, in_smem, correct, q_hits1);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
-extern "C" int mmx_lists_to_units(const int32_t* list_i, const int32_t* list_n, int n_shards, int64_t nq, int cap,
-                                  const int32_t* col2unit, int L, int32_t* list_t, int32_t* avail, cudaStream_t stream) {
-    MMX_REQUIRE(list_i && list_n && list_t && avail, "NULL argument");
-    MMX_REQUIRE(n_shards >= 1 && cap >= 1 && L >= 1 && L <= 1024, "bad list geometry");
-    if (nq == 0) return 0;
-    lists_to_units_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(list_i, list_n, n_shards, nq, cap, col2unit,
-                                                                           L, list_t, avail);
-    MMX_CHECK_CUDA(cudaGetLastError());
+extern "C" int mmx_boot_counts_lists_workspace_bytes(int B, int64_t n_units, size_t* bytes) {
+    MMX_REQUIRE(bytes != nullptr && B >= 0 && n_units > 0, "bad argument");
+    *bytes = (size_t)((B + CHUNK_B - 1) / CHUNK_B) * (size_t)n_units * CHUNK_B;
     return 0;
 }
 
-// K3 without a bitmask (LIST mode). list_t holds min(cnt_above[q], L) units of query q's above-GT set — all of it
-// when cnt_above[q] <= L. (iteration, query) pairs whose truncated list did not reach a multiplicity of 10 are left
-// out of `correct` and reported in unres [unres_cap, 2] / *unres_n (may exceed unres_cap: call again with more room).
-extern "C" int mmx_boot_counts_lists(const int32_t* list_t, int L, const int32_t* cnt_above, const int32_t* q_unit,
-                                     const uint8_t* mult, int B, int64_t n_units, int64_t nq, int32_t* correct,
-                                     int32_t* q_hits1, int32_t* unres, int32_t* unres_n, int unres_cap,
-                                     cudaStream_t stream) {
-    MMX_REQUIRE(list_t && cnt_above && mult && correct && unres && unres_n && unres_cap >= 1, "NULL argument");
+// K3 without a bitmask (LIST mode), straight from the per-shard lists of K1. The first min(cnt_above[q], L) entries of
+// query q's concatenated lists are walked — all of its above-GT set when cnt_above[q] <= L. (iteration, query) pairs whose
+// truncated list did not reach a multiplicity of 10 are left out of `correct` and reported in unres [unres_cap, 2] /
+// *unres_n (may exceed unres_cap: call again with more room).
+extern "C" int mmx_boot_counts_lists(const int32_t* list_i, const int32_t* list_n, int n_shards, int64_t nq, int cap,
+                                     const int32_t* col2unit, int L, const int32_t* cnt_above, const int32_t* q_unit,
+                                     const uint8_t* mult, int B, int64_t n_units, int32_t* correct, int32_t* q_hits1,
+                                     int32_t* unres, int32_t* unres_n, int unres_cap, void* workspace,
+                                     size_t workspace_bytes, cudaStream_t stream) {
+    MMX_REQUIRE(list_i && list_n && cnt_above && mult && correct && unres && unres_n && unres_cap >= 1, "NULL argument");
+    MMX_REQUIRE(n_shards >= 1 && cap >= 1 && L >= 1 && L <= cap, "bad list geometry (1 <= L <= cap: all hits may sit in one shard)");
     MMX_CHECK_CUDA(cudaMemsetAsync(unres_n, 0, sizeof(int32_t), stream));
     if (B == 0) return 0;
-    const int in_smem = n_units <= 200 * 1024;
-    const size_t smem = in_smem ? (size_t)((n_units + 15) & ~15ll) : 0;
-    if (smem > 48 * 1024 && first_use_on_device(&boot_tag))
-        MMX_CHECK_CUDA(cudaFuncSetAttribute(boot_counts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
-    boot_counts_kernel<<<B, 256, smem, stream>>>(list_t, L, cnt_above, nullptr, 0, nullptr, q_unit, mult, n_units, nq,
-                                                 in_smem, correct, q_hits1, unres, unres_n, unres_cap);
+    MMX_CHECK_CUDA(cudaMemsetAsync(correct, 0, (size_t)B * 3 * sizeof(int32_t), stream));
+    if (nq == 0) return 0;
+    size_t need = 0;
+    mmx_boot_counts_lists_workspace_bytes(B, n_units, &need);
+    MMX_REQUIRE(workspace != nullptr && workspace_bytes >= need, "workspace too small (mmx_boot_counts_lists_workspace_bytes)");
+    MMX_REQUIRE(((uintptr_t)workspace & 15) == 0, "workspace must be 16-byte aligned");
+    const int n_chunks = (B + CHUNK_B - 1) / CHUNK_B;
+    uint8_t* mult_t = static_cast<uint8_t*>(workspace);
+    transpose_mult_kernel<<<dim3((unsigned)((n_units + CHUNK_B - 1) / CHUNK_B), (unsigned)n_chunks), 256, 0, stream>>>(
+        mult, B, n_units, mult_t);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    int per_sm = 0;  // a persistent grid: every CTA resident at once, the warps stride over the queries
+    MMX_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, boot_counts_lists_kernel, 256, 0));
+    const long long resident = (long long)sm_count() * std::max(per_sm, 1);
+    const long long ctas = std::min<long long>((nq + 7) / 8, std::max<long long>(resident / n_chunks, 1));
+    boot_counts_lists_kernel<<<dim3((unsigned)ctas, (unsigned)n_chunks), 256, 0, stream>>>(
+        list_i, list_n, n_shards, nq, cap, col2unit, L, cnt_above, q_unit, mult_t, B, n_units, correct, q_hits1, unres,
+        unres_n, unres_cap);
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

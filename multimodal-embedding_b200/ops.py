@@ -467,19 +467,19 @@ def boot_counts_lists_raw(r: ProtocolRanks, mult: torch.Tensor, q_hits1: Optiona
     B, n_units = mult.shape
     h = _lib.lib()
     dev = mult.device
-    list_t = torch.empty((L, nq), dtype=torch.int32, device=dev)
-    avail = torch.empty((nq,), dtype=torch.int32, device=dev)
-    _lib.check(h.mmx_lists_to_units(r.list_i.data_ptr(), r.list_n.data_ptr(), n_shards, nq, cap, _ptr(r.col2unit), L,
-                                    list_t.data_ptr(), avail.data_ptr(), _stream()))
+    need = ctypes.c_size_t()
+    _lib.check(h.mmx_boot_counts_lists_workspace_bytes(B, n_units, ctypes.byref(need)))
+    ws = torch.empty(max(need.value, 16), dtype=torch.uint8, device=dev)      # the transposed multiplicities
     correct = torch.empty((B, 3), dtype=torch.int32, device=dev)
     unres_cap = UNRESOLVED_CAP
     while True:
         unres = torch.empty((unres_cap, 2), dtype=torch.int32, device=dev)
         unres_n = torch.empty((1,), dtype=torch.int32, device=dev)
         hits = None if q_hits1 is None else q_hits1.clone()
-        _lib.check(h.mmx_boot_counts_lists(list_t.data_ptr(), L, r.cnt_above.data_ptr(), _ptr(r.q_unit), mult.data_ptr(),
-                                           B, n_units, nq, correct.data_ptr(), _ptr(hits), unres.data_ptr(),
-                                           unres_n.data_ptr(), unres_cap, _stream()))
+        _lib.check(h.mmx_boot_counts_lists(r.list_i.data_ptr(), r.list_n.data_ptr(), n_shards, nq, cap, _ptr(r.col2unit), L,
+                                           r.cnt_above.data_ptr(), _ptr(r.q_unit), mult.data_ptr(), B, n_units,
+                                           correct.data_ptr(), _ptr(hits), unres.data_ptr(), unres_n.data_ptr(),
+                                           unres_cap, ws.data_ptr(), ws.numel(), _stream()))
         n_un = int(unres_n.item())
         if n_un <= unres_cap:
             break
@@ -619,23 +619,32 @@ class DeviceRng:
     def _table_for(self, raw_words: float):
         return self._par_buffers(long=raw_words >= self.LONG_MIN_WORDS)
 
-    def randint(self, high: int, count: int, parallel: Optional[bool] = None) -> torch.Tensor:
+    def randint(self, high: int, count: int, parallel: Optional[bool] = None,
+                window: Optional[Tuple[int, int]] = None) -> Optional[torch.Tensor]:
         """The next `count` values of ``randint(0, high)``. Large requests use the jump-ahead kernels (K6p, all SMs),
-        small ones the single-CTA kernel (K6); both continue the same stream, so they can be mixed freely."""
-        out = torch.empty((count,), dtype=torch.int32, device=self.state.device)
+        small ones the single-CTA kernel (K6); both continue the same stream, so they can be mixed freely.
+        window=(begin, n): the generator advances by all `count` values but only values [begin, begin + n) are kept
+        and returned (None when n == 0) — a rank's block of a stream every rank replays, or a plain skip."""
+        dev = self.state.device
+        if window is None:
+            window = (0, count)
+        w0, wn = int(window[0]), int(window[1])
+        if w0 < 0 or wn < 0 or w0 + wn > count:
+            raise ValueError("window outside the request")
         if parallel is None:
             parallel = count >= self.PAR_MIN_COUNT
         if parallel:
             from . import mtjump
+            out = torch.empty((wn,), dtype=torch.int32, device=dev) if wn else None
             mask = (1 << max(int(high) - 1, 1).bit_length()) - 1                   # numpy's masked rejection
             polys, scratch, _, _, seg_blocks = self._table_for(count * (mask + 1.0) / float(high))
-            _lib.check(_lib.lib().mmx_mt19937_randint_par(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
-                                                          polys.data_ptr(), mtjump.N_POLY, seg_blocks,
-                                                          scratch.data_ptr(), scratch.numel(), _stream()))
-        else:
-            _lib.check(_lib.lib().mmx_mt19937_randint(self.state.data_ptr(), int(high), int(count), out.data_ptr(),
-                                                      _stream()))
-        return out
+            _lib.check(_lib.lib().mmx_mt19937_randint_par_window(
+                self.state.data_ptr(), int(high), int(count), _ptr(out), w0, wn, polys.data_ptr(), mtjump.N_POLY,
+                seg_blocks, scratch.data_ptr(), scratch.numel(), _stream()))
+            return out
+        out = torch.empty((count,), dtype=torch.int32, device=dev)
+        _lib.check(_lib.lib().mmx_mt19937_randint(self.state.data_ptr(), int(high), int(count), out.data_ptr(), _stream()))
+        return out[w0:w0 + wn] if wn else None
 
     def raw_words(self, count: int, advance: bool = True) -> Optional[torch.Tensor]:
         """The next `count` raw 32-bit outputs (as int32 bit patterns). advance=False leaves the generator where it

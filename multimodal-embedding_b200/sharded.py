@@ -48,6 +48,19 @@ def merge_thresholds(thr: torch.Tensor, group=None) -> torch.Tensor:
     return thr
 
 
+def _all_gather_stacked(mine: torch.Tensor, group=None) -> torch.Tensor:
+    """[world, *mine.shape]: every rank's equally shaped tensor, gathered straight into one buffer (NCCL: no staging copy;
+    the list form is kept for the gloo host-logic tests)."""
+    world = dist.get_world_size(group)
+    mine = mine.contiguous()
+    out = torch.empty((world,) + tuple(mine.shape), dtype=mine.dtype, device=mine.device)
+    if mine.is_cuda:
+        dist.all_gather_into_tensor(out, mine, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), mine, group=group)
+    return out
+
+
 def merge_ranks(local: ProtocolRanks, bounds: List[Tuple[int, int]], group=None) -> ProtocolRanks:
     """ONE all-gather per scoring pass: every shard's bit columns travel once, each rank then shifts them to
     their global bit offsets, ORs them together and takes the merged rows' popcounts as the counts (mmx_place_bit_columns;
@@ -60,30 +73,29 @@ def merge_ranks(local: ProtocolRanks, bounds: List[Tuple[int, int]], group=None)
     if local.bits is not None:
         nq = local.bits.shape[0]
         wmax = max((e - b + 31) // 32 for b, e in bounds)
-        gathered = torch.empty((world, nq, wmax), dtype=local.bits.dtype, device=local.bits.device)
         mine = local.bits
         if mine.shape[1] != wmax:
             mine = torch.zeros((nq, wmax), dtype=local.bits.dtype, device=local.bits.device)
             mine[:, : local.bits.shape[1]] = local.bits
-        dist.all_gather(list(gathered.unbind(0)), mine.contiguous(), group=group)
+        gathered = _all_gather_stacked(mine, group)
         if gathered.is_cuda:
             from . import ops
             bits, cnt = ops.place_bit_columns(gathered, bounds)
         else:                                            # gloo host-logic tests: the same merge in torch
             bits = place_bit_columns(list(gathered.unbind(0)), bounds)
             cnt = _popcount_rows(bits)
-    else:
+    elif local.list_i is None:
         cnt = local.cnt_above.clone()
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     list_i = list_n = None
     if local.list_i is not None:
-        # LIST mode: ONE all-gather of a fixed-size record per query — the shard's `cap` column ids and its cursor
-        cap = local.list_i.shape[2]
-        rec = torch.cat([local.list_i[0], local.list_n[0][:, None]], dim=1).contiguous()      # [nq, cap + 1]
-        parts = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(parts, rec, group=group)
-        list_i = torch.stack([p[:, :cap] for p in parts]).contiguous()
-        list_n = torch.stack([p[:, cap] for p in parts]).contiguous()
+        # LIST mode: two all-gathers, both straight into the layout K3 reads — the shards' column lists [world, nq, cap]
+        # (the bulk: no packing or unpacking copies of a 2 GB record array) and one small (exact count, cursor) pair per
+        # query, whose first column summed over the shards is the global count (no separate all-reduce)
+        list_i = _all_gather_stacked(local.list_i[0], group)
+        meta = _all_gather_stacked(torch.stack([local.cnt_above, local.list_n[0]], dim=1), group)     # [world, nq, 2]
+        cnt = meta[:, :, 0].sum(dim=0, dtype=torch.int32)
+        list_n = meta[:, :, 1].contiguous()
     return ProtocolRanks(thr=local.thr, cnt_above=cnt, bits=bits, n_cols=bounds[-1][1], col2unit=local.col2unit,
                          q_unit=local.q_unit, list_i=list_i, list_n=list_n)
 
@@ -197,31 +209,49 @@ def list_boot_fn(recount, group=None, stats: Optional[dict] = None):
     return fn
 
 
+def stats_block(n_iterations: int, group=None) -> Tuple[int, int]:
+    """[b0, b1): the bootstrap iterations this rank takes when the statistics are split over the ranks."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    per = -(-n_iterations // world)
+    return min(n_iterations, rank * per), min(n_iterations, (rank + 1) * per)
+
+
 def bootstrap_stats(ranks: ProtocolRanks, sample_indices: torch.Tensor, ci_idx: torch.Tensor, q_unit: torch.Tensor,
-                    n_units: int, group=None, boot_fn=None):
+                    n_units: int, group=None, boot_fn=None, mark=None, n_iterations: Optional[int] = None):
     """The statistics tail of a sharded pass — K3 over the bootstrap iterations, K4 over the CI resample rows — split
     over the ranks instead of serialised on rank 0: every rank holds the merged rank structures and the same numpy
     stream (sample_indices int32 [B, n_units], ci_idx int32 [M, R, B]), takes its block of iterations / resample rows,
-    and two small all-gathers put the pieces together. Returns (values fp64 [B, M], means fp64 [M, R]) on every rank,
+    and two small all-gathers put the pieces together. With n_iterations = B given, sample_indices holds only THIS
+    rank's rows (stats_block(B): DeviceRng.randint(window=...) keeps just those). Returns (values fp64 [B, M], means fp64 [M, R]) on every rank,
     bit-identical to the single-GPU tail (integer counts; the means are computed row by row either way).
-    boot_fn(ranks, mult) -> int32 [b, M] defaults to ops.boot_counts."""
+    boot_fn(ranks, mult) -> int32 [b, M] defaults to ops.boot_counts. mark(name) (optional) is called after every phase
+    (api.run_retrieval_bootstrap records a CUDA event there when timings are asked for)."""
     from . import ops
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     boot_fn = boot_fn or ops.boot_counts
-    B = sample_indices.shape[0]
+    mark = mark or (lambda name: None)
+    own_rows_only = n_iterations is not None
+    B = n_iterations if own_rows_only else sample_indices.shape[0]
     per = -(-B // world)
     b0, b1 = min(B, rank * per), min(B, (rank + 1) * per)
+    if own_rows_only and sample_indices.shape[0] != b1 - b0:
+        raise ValueError("sample_indices must hold this rank's block of iterations (stats_block)")
     dev = sample_indices.device
     rec = torch.zeros((per, 4), dtype=torch.int64, device=dev)       # correct@1/5/10 + query copies drawn
     if b1 > b0:
-        mult = ops.bincount(sample_indices[b0:b1].contiguous(), n_units)
+        mult = ops.bincount(sample_indices if own_rows_only else sample_indices[b0:b1].contiguous(), n_units)
+        mark("bincount")
         rec[: b1 - b0, :3] = boot_fn(ranks, mult)
+        mark("bootstrap_counts")
         rec[: b1 - b0, 3] = mult[:, q_unit.long()].sum(dim=1, dtype=torch.int64)
+        mark("query_copies_drawn")
     if world > 1:
         allrec = torch.empty((world, per, 4), dtype=torch.int64, device=dev)
         dist.all_gather(list(allrec.unbind(0)), rec, group=group)
         rec = allrec.view(world * per, 4)
+        mark("counts_all_gather")
     rec = rec[:B]
     values = 100.0 * rec[:, :3].to(torch.float64) / rec[:, 3:4].to(torch.float64)         # main.py:358, IEEE division
     M, R, _ = ci_idx.shape
@@ -234,6 +264,7 @@ def bootstrap_stats(ranks: ProtocolRanks, sample_indices: torch.Tensor, ci_idx: 
         allm = torch.empty((world, M, perr), dtype=torch.float64, device=dev)
         dist.all_gather(list(allm.unbind(0)), means, group=group)
         means = allm.permute(1, 0, 2).reshape(M, world * perr)
+    mark("ci_means_and_all_gather")
     return values, means[:, :R].contiguous()
 
 

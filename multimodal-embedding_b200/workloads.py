@@ -231,7 +231,8 @@ def cfg3_section(dev: torch.device, group=None, n: int = 1_000_000, d: int = 102
                       "tflops_per_gpu_count_list_pass": k1_tf,
                       "frac_of_bf16_peak": k1_tf / peak_tflops if peak_tflops else None,
                       "pairs_per_s": n * n / (t2i_ms * 1e-3), "base_R@1/5/10": [row["base"][k] for k in (1, 5, 10)],
-                      "R@1_ci": [row["R@1_mean"], row["R@1_lower"], row["R@1_upper"]], "list_mode": row.get("_list_mode")}
+                      "R@1_ci": [row["R@1_mean"], row["R@1_lower"], row["R@1_upper"]], "list_mode": row.get("_list_mode"),
+                      "device_ms_by_phase_rank0": tm.get("device_ms"), "host_checkpoints_ms_rank0": tm.get("wall_ms")}
     del txt, G, thr
     torch.cuda.empty_cache()
     if i2t:

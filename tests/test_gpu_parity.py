@@ -485,6 +485,53 @@ def test_device_rng_jump_ahead_starved_budget(mmx_mod):
     assert rs_dev.randint(0, 1 << 30) == rs_ref.randint(0, 1 << 30)
 
 
+@pytest.mark.parametrize("high,count,windows", [
+    (5000, 3_000_000, [(0, 0), (0, 3_000_000), (123_457, 1000), (2_999_995, 5), (1_500_000, 700_001)]),
+    (1_000_000, 30_000_000, [(11_000_003, 4_000_000), (29_000_000, 1_000_000), (0, 0)]),   # 64-block table, chained launches
+    (100_000, 130_000_000, [(16_250_000, 16_250_000), (113_750_000, 16_250_000)]),        # 512-block table (cfg5's draws)
+])
+def test_device_rng_window_keeps_a_block_of_the_stream(mmx_mod, high, count, windows):
+    """randint(window=(begin, n)): the rows a rank keeps of a stream every rank replays (sharded bootstrap: iterations
+    [b0, b1) of main.py:586-588) == that slice of numpy's full draw; the generator ends where numpy's does. (0, 0) = skip."""
+    ref = np.random.RandomState(31)
+    ref.randint(0, 7, size=401)
+    start = ref.get_state()
+    want = ref.randint(0, high, size=count)
+    end_probe = ref.randint(0, 1 << 30)
+    for w0, wn in windows:
+        rs = np.random.RandomState()
+        rs.set_state(start)
+        d = mmx_mod.ops.DeviceRng(rs)
+        got = d.randint(high, count, parallel=True, window=(w0, wn))
+        d.commit()
+        if wn == 0:
+            assert got is None
+        else:
+            assert got.shape == (wn,) and np.array_equal(got.cpu().numpy().astype(np.int64), want[w0:w0 + wn])
+        assert rs.randint(0, 1 << 30) == end_probe
+
+
+def test_device_rng_window_starved_budget(mmx_mod):
+    """The sequential finish of a request that outran its budget honours the window too."""
+    h = mmx_mod._lib.lib()
+    ref = np.random.RandomState(8)
+    want = ref.randint(0, 5000, size=1_000_000)
+    try:
+        mmx_mod._lib.check(h.mmx_mt19937_par_set_slack(0.80, 0.0))
+        for w0, wn in ((0, 0), (990_000, 10_000), (400_000, 300_000)):
+            rs = np.random.RandomState(8)
+            d = mmx_mod.ops.DeviceRng(rs)
+            got = d.randint(5000, 1_000_000, parallel=True, window=(w0, wn))
+            d.commit()
+            if wn:
+                assert np.array_equal(got.cpu().numpy().astype(np.int64), want[w0:w0 + wn])
+            chk = np.random.RandomState(8)
+            chk.randint(0, 5000, size=1_000_000)
+            assert np.array_equal(rs.get_state()[1], chk.get_state()[1]) and rs.get_state()[2] == chk.get_state()[2]
+    finally:
+        mmx_mod._lib.check(h.mmx_mt19937_par_set_slack(1.02, 64.0))
+
+
 @pytest.mark.parametrize("n,n_shuffles", [(2, 9), (3, 40), (5, 300), (64, 120), (600, 300), (2000, 150), (4096, 12), (10000, 7), (16384, 3)])
 def test_device_shuffle_matches_numpy_cumulative_shuffles(mmx_mod, n, n_shuffles):
     """K6s: the index array after every one of numpy's cumulative in-place shuffles (main.py:296), the number of
@@ -736,6 +783,56 @@ def test_dense_rank_lists_hold_the_above_gt_set(mmx_mod):
             assert n == min(int(cnt[q]), cap) and (int(ln[q]) > cap) == (int(cnt[q]) > cap)
             cols = li[q, :n]
             assert above[q, cols].all() and len(set(cols.tolist())) == n
+
+
+@pytest.mark.parametrize("n_shards,nq,cap,L,B,n_units", [(1, 300, 8, 8, 40, 300), (3, 700, 8, 8, 300, 257), (8, 1500, 64, 64, 125, 4000),
+                                                       (2, 97, 40, 33, 129, 50)])
+def test_boot_counts_lists_kernel_vs_numpy(mmx_mod, n_shards, nq, cap, L, B, n_units):
+    """K3 in LIST mode (one warp per query, iterations across the lanes, transposed multiplicities) on hand-made per-shard
+    lists with a column->unit map, a query->unit map, cursors beyond the capacity, several 128-iteration chunks: the sums
+    of min(m_q, max(0, k - c)), the per-query R@1 hits and the set of unsettled (iteration, query) pairs ==
+    a literal numpy walk."""
+    dev = _dev()
+    ops = mmx_mod.ops
+    rs = np.random.RandomState(nq + B)
+    n_cols = 3 * n_units
+    col2unit = rs.randint(0, n_units, size=n_cols).astype(np.int32)
+    q_unit = rs.randint(0, n_units, size=nq).astype(np.int32)
+    n_true = rs.poisson(0.45 * cap, size=(n_shards, nq)).astype(np.int32)          # a shard's exact hit count
+    n_true[:, rs.rand(nq) < 0.3] = 0
+    n_true[0, rs.rand(nq) < 0.2] += 2 * cap
+    list_n = n_true + (n_true > cap) * rs.randint(0, 3, size=n_true.shape).astype(np.int32)   # the cursor stops somewhere above cap
+    list_i = rs.randint(0, n_cols, size=(n_shards, nq, cap)).astype(np.int32)
+    cnt = n_true.sum(axis=0).astype(np.int32)
+    mult = np.minimum(rs.poisson(0.8, size=(B, n_units)), 255).astype(np.uint8)
+    mult[:, rs.rand(n_units) < 0.02] = 200                                         # saturating byte sums
+    r = ops.ProtocolRanks(thr=torch.zeros(nq, device=dev), cnt_above=torch.from_numpy(cnt).to(dev), bits=None, n_cols=n_cols,
+                          col2unit=torch.from_numpy(col2unit).to(dev), q_unit=torch.from_numpy(q_unit).to(dev),
+                          list_i=torch.from_numpy(list_i).to(dev), list_n=torch.from_numpy(list_n).to(dev))
+    hits = torch.zeros(nq, dtype=torch.int32, device=dev)
+    correct, pairs = ops.boot_counts_lists_raw(r, torch.from_numpy(mult).to(dev), q_hits1=hits, list_len=L)
+    want = np.zeros((B, 3), dtype=np.int64)
+    want_hits = np.zeros(nq, dtype=np.int64)
+    want_pairs = set()
+    units = []
+    for q in range(nq):
+        ent = np.concatenate([col2unit[list_i[s, q, : min(list_n[s, q], cap)]] for s in range(n_shards)])
+        units.append(ent[: min(cnt[q], L)])
+    for q in range(nq):
+        mq = mult[:, q_unit[q]].astype(np.int64)
+        c = mult[:, units[q]].astype(np.int64).sum(axis=1) if len(units[q]) else np.zeros(B, dtype=np.int64)
+        unsettled = (mq > 0) & (c < 10) & (cnt[q] > L)
+        want_pairs.update((int(b), q) for b in np.nonzero(unsettled)[0])
+        ok = (mq > 0) & ~unsettled
+        for j, k in enumerate((1, 5, 10)):
+            h = np.where(ok, np.minimum(mq, np.maximum(0, k - c)), 0)
+            want[:, j] += h
+            if k == 1:
+                want_hits[q] = h.sum()
+    assert np.array_equal(correct.cpu().numpy(), want)
+    assert np.array_equal(hits.cpu().numpy(), want_hits)
+    got_pairs = set() if pairs is None else {(int(b), int(q)) for b, q in pairs.cpu().numpy()}
+    assert got_pairs == want_pairs and (len(want_pairs) > 0 or cap >= 64)
 
 
 def test_list_mode_bootstrap_equals_bitmask_mode(mmx_mod):
