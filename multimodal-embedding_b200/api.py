@@ -836,7 +836,7 @@ def run_retrieval_bootstrap(queries, docs, query_to_doc: Sequence[int], m_info: 
         else:
             correct = ops.boot_counts(ranks, mult)                                                   # [B, 3] int32
         # query copies drawn in each iteration (integer sum: the same doubles as summing float64 copies)
-        denom = mult[:, gt_idx.long()].sum(dim=1, dtype=torch.int64).to(torch.float64)
+        denom = ops.query_copies_drawn(mult, gt_idx).to(torch.float64)
         values = 100.0 * correct.to(torch.float64) / denom[:, None]                                  # main.py:358
         means = ops.ci_means_batched(values.t().contiguous(), ci_idx)                                # three CIs, one launch
     else:

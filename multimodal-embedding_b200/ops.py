@@ -457,6 +457,14 @@ def boot_counts(r: ProtocolRanks, mult: torch.Tensor, list_len: int = LIST_LEN,
     return correct
 
 
+def query_copies_drawn(mult: torch.Tensor, q_unit: torch.Tensor) -> torch.Tensor:
+    """int64 [B]: how many query copies each bootstrap iteration drew = sum_q mult[b, q_unit[q]] — the denominator of
+    main.py:358's recall (len(valid_indices)). Computed as sum_u mult[b, u] * (#queries of unit u): one pass over mult
+    instead of a [B, n_queries] gather."""
+    per_unit = torch.bincount(q_unit.long(), minlength=mult.shape[1]).to(torch.int32)
+    return (mult.to(torch.int32) * per_unit[None, :]).sum(dim=1, dtype=torch.int64)
+
+
 def boot_counts_lists_raw(r: ProtocolRanks, mult: torch.Tensor, q_hits1: Optional[torch.Tensor] = None,
                           list_len: Optional[int] = None):
     """K3 in LIST mode without the exact recount: returns (correct int32 [B, 3] WITHOUT the unsettled pairs' share,
