@@ -329,8 +329,9 @@ def run_ours(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(k2_ms, op=dist.ReduceOp.MAX)
     ms_per_step, k2_ms = float(ms.item()), float(k2_ms.item())
-    # K2 (tok2q, maxsim, fixup) + KR (2) + shard merge (1, N > 1) + bincount (2) + K3 (2) + K4 (1), on every rank
-    launches_per_step = 3 + 2 + (1 if world > 1 else 0) + 2 + 2 + 1
+    # K2 (tok2q, maxsim, fixup) + KR (2) + shard merge (1, N > 1) + bincount (2) + K3 (2) + copies drawn (1) + K4 (1), on
+    # every rank
+    launches_per_step = 3 + 2 + (1 if world > 1 else 0) + 2 + 2 + 1 + 1
 
     # ---- e2e: the public API from pinned host buffers (H2D + host RNG + D2H inside the timed region), wall clock
     Qh = torch.empty(Q.shape, dtype=Q.dtype, pin_memory=True).copy_(Q)

@@ -136,6 +136,10 @@ int mmx_above_lists(const uint32_t* above_bits, int64_t nq, int64_t words_per_ro
 int mmx_boot_counts(const int32_t* list_t, int L, const int32_t* cnt_above, const uint32_t* above_bits,
                     int64_t words_per_row, const int32_t* col2unit, const int32_t* q_unit, const uint8_t* mult, int B,
                     int64_t n_units, int64_t nq, int32_t* correct, int32_t* q_hits1, cudaStream_t stream);
+/* drawn int64 [B] = sum_q mult[b, q_unit[q]] (q_unit nullable = identity): the query copies iteration b drew — the
+ * len(valid_indices) every recall of main.py:358/368/378 is divided by. */
+int mmx_copies_drawn(const uint8_t* mult, int B, int64_t n_units, const int32_t* q_unit, int64_t nq, int64_t* drawn,
+                     cudaStream_t stream);
 
 /* Shard merge of the above-GT bitmask (the counts and bit columns of main.py:331-378's rank tests are additive /
  * concatenable over gallery shards). gathered uint32 [n_shards, nq, wmax] = every shard's bit columns as ONE all-gather

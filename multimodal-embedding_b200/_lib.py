@@ -123,6 +123,7 @@ _SIGNATURES = {
         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int64,  # col2unit, q_unit, mult, B, n_units
         _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p,            # nq, correct, q_hits1, stream
     ]),
+    "mmx_copies_drawn": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p]),
     "mmx_dense_rank_lists": (_c.c_int, [
         _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int64,   # Q, nq, G, ng, d, g_base
         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p,  # thr, cnt_above, list_i, list_n, cap, stream

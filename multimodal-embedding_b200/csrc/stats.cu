@@ -31,6 +31,26 @@ __global__ void saturate_u8_kernel(const int32_t* __restrict__ counts, long long
     if (i < n) out[i] = (uint8_t)min(counts[i], 255);
 }
 
+// drawn[b] = sum_q mult[b, q_unit[q]]: the query copies iteration b drew (the denominator of main.py:358's recall).
+// One CTA per iteration; the iteration's multiplicity row (n_units bytes) stays in L1/L2 while the queries stream by.
+__global__ void __launch_bounds__(256)
+copies_drawn_kernel(const uint8_t* __restrict__ mult, long long n_units, const int32_t* __restrict__ q_unit,
+                    long long nq, long long* __restrict__ drawn) {
+    __shared__ long long red[8];
+    const uint8_t* mrow = mult + (long long)blockIdx.x * n_units;
+    long long sum = 0;
+    for (long long q = threadIdx.x; q < nq; q += blockDim.x) sum += mrow[q_unit != nullptr ? q_unit[q] : q];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long tot = 0;
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        drawn[blockIdx.x] = tot;
+    }
+}
+
 // ------------------------------------------------------------------------------------------- above-GT lists
 // list_t[i * nq + q] = unit (col2unit applied) of the i-th set bit of row q, for i < min(cnt, L). One warp per row.
 __global__ void above_lists_kernel(const uint32_t* __restrict__ bits, long long nq, long long wpr,
@@ -535,6 +555,15 @@ extern "C" int mmx_bincount(const int32_t* sample_idx, int B, int64_t n_draws, i
     }
     const long long n = (long long)B * n_units;
     saturate_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(scratch, n, mult);
+    MMX_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mmx_copies_drawn(const uint8_t* mult, int B, int64_t n_units, const int32_t* q_unit, int64_t nq,
+                                int64_t* drawn, cudaStream_t stream) {
+    MMX_REQUIRE(mult != nullptr && drawn != nullptr && B >= 0 && n_units > 0 && nq >= 0, "bad argument");
+    if (B == 0) return 0;
+    copies_drawn_kernel<<<B, 256, 0, stream>>>(mult, n_units, q_unit, nq, reinterpret_cast<long long*>(drawn));
     MMX_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -457,12 +457,15 @@ def boot_counts(r: ProtocolRanks, mult: torch.Tensor, list_len: int = LIST_LEN,
     return correct
 
 
-def query_copies_drawn(mult: torch.Tensor, q_unit: torch.Tensor) -> torch.Tensor:
-    """int64 [B]: how many query copies each bootstrap iteration drew = sum_q mult[b, q_unit[q]] — the denominator of
-    main.py:358's recall (len(valid_indices)). Computed as sum_u mult[b, u] * (#queries of unit u): one pass over mult
-    instead of a [B, n_queries] gather."""
-    per_unit = torch.bincount(q_unit.long(), minlength=mult.shape[1]).to(torch.int32)
-    return (mult.to(torch.int32) * per_unit[None, :]).sum(dim=1, dtype=torch.int64)
+def query_copies_drawn(mult: torch.Tensor, q_unit: Optional[torch.Tensor], nq: Optional[int] = None) -> torch.Tensor:
+    """int64 CUDA [B]: how many query copies each bootstrap iteration drew = sum_q mult[b, q_unit[q]] — the denominator of
+    main.py:358's recall (len(valid_indices)). q_unit None = identity over nq queries."""
+    _need_cuda(mult)
+    B, n_units = mult.shape
+    n = int(q_unit.shape[0]) if q_unit is not None else int(nq)
+    out = torch.empty((B,), dtype=torch.int64, device=mult.device)
+    _lib.check(_lib.lib().mmx_copies_drawn(mult.data_ptr(), B, n_units, _ptr(q_unit), n, out.data_ptr(), _stream()))
+    return out
 
 
 def boot_counts_lists_raw(r: ProtocolRanks, mult: torch.Tensor, q_hits1: Optional[torch.Tensor] = None,

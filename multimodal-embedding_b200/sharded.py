@@ -245,7 +245,8 @@ def bootstrap_stats(ranks: ProtocolRanks, sample_indices: torch.Tensor, ci_idx: 
         mark("bincount")
         rec[: b1 - b0, :3] = boot_fn(ranks, mult)
         mark("bootstrap_counts")
-        rec[: b1 - b0, 3] = ops.query_copies_drawn(mult, q_unit)
+        rec[: b1 - b0, 3] = (ops.query_copies_drawn(mult, q_unit) if mult.is_cuda      # (CPU: the gloo host-logic tests)
+                             else mult[:, q_unit.long()].sum(dim=1, dtype=torch.int64))
         mark("query_copies_drawn")
     if world > 1:
         allrec = torch.empty((world, per, 4), dtype=torch.int64, device=dev)

@@ -831,6 +831,10 @@ def test_boot_counts_lists_kernel_vs_numpy(mmx_mod, n_shards, nq, cap, L, B, n_u
                 want_hits[q] = h.sum()
     assert np.array_equal(correct.cpu().numpy(), want)
     assert np.array_equal(hits.cpu().numpy(), want_hits)
+    mult_d = torch.from_numpy(mult).to(dev)
+    assert np.array_equal(ops.query_copies_drawn(mult_d, r.q_unit).cpu().numpy(), mult[:, q_unit].astype(np.int64).sum(axis=1))
+    assert np.array_equal(ops.query_copies_drawn(mult_d, None, nq=min(nq, n_units)).cpu().numpy(),
+                          mult[:, : min(nq, n_units)].astype(np.int64).sum(axis=1))
     got_pairs = set() if pairs is None else {(int(b), int(q)) for b, q in pairs.cpu().numpy()}
     assert got_pairs == want_pairs and (len(want_pairs) > 0 or cap >= 64)
 
