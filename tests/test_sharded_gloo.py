@@ -60,6 +60,8 @@ def _worker(rank, world, port, n_cols, out_dir):
     cnt_full, bits_full = _local_structures(scores, gt_sets, 0, n_cols, thr_full)
     ok = (torch.equal(thr, thr_full) and torch.equal(merged.cnt_above, cnt_full)
           and torch.equal(merged.bits, bits_full) and merged.n_cols == n_cols)
+    # the ranks' blocks of bootstrap iterations tile [0, B) (each rank keeps only those rows of the numpy stream)
+    ok = ok and mmx.sharded.stats_block(1001) == ((0, 501), (501, 1001))[rank] and mmx.sharded.stats_block(1) == ((0, 1), (1, 1))[rank]
     Path(out_dir, f"ok{rank}").write_text("1" if ok else "0")
     dist.barrier()
     dist.destroy_process_group()
