@@ -65,8 +65,16 @@ def synth_colpali_shard(dev: torch.device, nq: int, nd: int, lq: int, ld: int, d
     mine = (q2d >= d0) & (q2d < d1)
     qi = torch.nonzero(mine).squeeze(1)
     if qi.numel():
-        dst = ((q2d[qi] - d0) * ld)[:, None] + rows[qi]                   # [n_mine, lq] flat patch rows
-        D[dst.reshape(-1)] = planted[qi].reshape(-1, dim)                  # duplicates: the last token written wins
+        dst = (((q2d[qi] - d0) * ld)[:, None] + rows[qi]).reshape(-1)     # flat patch row of every planted token
+        src = planted[qi].reshape(-1, dim)
+        # two tokens may land on the same patch row: the LAST one (query order, then token order) wins — decided by a sort,
+        # not by the scatter's write order, so the corpus is the same at every shard count and in every run
+        order = torch.arange(dst.numel(), device=dev, dtype=torch.int64)
+        perm = torch.sort(dst * dst.numel() + order).indices
+        ds = dst[perm]
+        last = torch.ones_like(ds, dtype=torch.bool)
+        last[:-1] = ds[1:] != ds[:-1]
+        D[ds[last]] = src[perm[last]]
     return Q.bfloat16().contiguous(), D, q2d.to(torch.int32)
 
 
